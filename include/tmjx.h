@@ -1,0 +1,191 @@
+/*
+ * tmjx.h — C ABI of the B200-native rodent-tracking environment step.
+ *
+ * This is the drop-in boundary for the one hot path this repository replaces: the batched
+ * `reset` / `step` of track-mjx's motion-tracking environment, i.e. the work behind
+ *
+ *   SingleClipTracking.reset_from_clip   reference track_mjx/environment/task/single_clip_tracking.py:121-205
+ *   SingleClipTracking.step              reference track_mjx/environment/task/single_clip_tracking.py:207-320
+ *   MultiClipTracking.reset / _get_reference_clip   reference .../task/multi_clip_tracking.py:74-109
+ *   compute_tracking_rewards             reference track_mjx/environment/task/reward.py:359-485
+ *   BaseWalker.compute_local_*           reference track_mjx/environment/walker/base.py:170-258
+ *   PipelineEnv.pipeline_init/step -> brax.mjx.pipeline.init/step -> mujoco.mjx.forward/step
+ *                                        (upstream brax 0.12.3 / mujoco-mjx 3.3.2, called at
+ *                                         single_clip_tracking.py:163 and :219)
+ *   auto-reset + episode wrapper         reference track_mjx/environment/wrappers.py:104-144, 288-310
+ *
+ * The reference has no FFI of its own: it is pure Python/JAX and the XLA program is the
+ * "operator".  A maintainer binds these entry points either through an XLA-FFI handler
+ * (csrc/tmjx_xla_ffi.cc, built only when jaxlib's headers exist) or through ctypes
+ * (track-mjx_b200/_lib.py); INTEGRATION.md shows both.
+ *
+ * Conventions
+ *   - plain C types only; all array pointers in TmjxState / TmjxOut / `action` are DEVICE pointers,
+ *     row-major `[n_env, dim]` fp32 (int32 for indices) — the layout `jax.vmap` gives the same leaves;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *     synchronisation, re-entrant; errors are returned as negative codes, text via tmjx_last_error();
+ *   - simulation failure is never an error: NaNs raise `done` exactly as the reference does
+ *     (single_clip_tracking.py:286-293).
+ */
+#ifndef TMJX_H_
+#define TMJX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMJX_ABI_VERSION 1
+#define TMJX_MAX_IDX 80      /* upper bound on the walker index tables */
+#define TMJX_N_METRICS 20    /* single_clip_tracking.py:176-197 */
+
+enum { TMJX_OK = 0, TMJX_E_ARG = -1, TMJX_E_BLOB = -2, TMJX_E_CUDA = -3, TMJX_E_UNSUPPORTED = -4 };
+enum { TMJX_SOLVER_CG = 0, TMJX_SOLVER_NEWTON = 1 };
+
+/* order of TmjxOut.metrics columns == insertion order of the reference's metrics dict */
+enum {
+  TMJX_M_POS_REWARD = 0, TMJX_M_QUAT_REWARD, TMJX_M_JOINT_REWARD, TMJX_M_ANGVEL_REWARD, TMJX_M_BODYPOS_REWARD,
+  TMJX_M_ENDEFF_REWARD, TMJX_M_CTRL_COST, TMJX_M_CTRL_DIFF_COST, TMJX_M_ENERGY_COST, TMJX_M_DONE, TMJX_M_TOO_FAR,
+  TMJX_M_BAD_POSE, TMJX_M_BAD_QUAT, TMJX_M_FALL, TMJX_M_NAN, TMJX_M_JOINT_DISTANCE, TMJX_M_SUMMED_POS_DISTANCE,
+  TMJX_M_QUAT_DISTANCE, TMJX_M_VAR_COST, TMJX_M_JERK_COST
+};
+
+/* Task constants: the kwargs of MultiClipTracking.__init__ (multi_clip_tracking.py:16-31), RewardConfig
+ * (reward.py:15-54) and the walker index tables (walker/rodent.py:89-114). */
+typedef struct TmjxTaskConfig {
+  int32_t abi_version;                 /* TMJX_ABI_VERSION */
+  /* env_args */
+  int32_t physics_steps_per_control_step;
+  int32_t solver;                      /* TMJX_SOLVER_* */
+  int32_t iterations;
+  int32_t ls_iterations;
+  float mj_model_timestep;
+  float mocap_hz;
+  int32_t clip_length;
+  int32_t traj_length;
+  int32_t episode_length;              /* brax EpisodeWrapper limit (train.py:221-225); used only with TMJX_F_AUTORESET */
+  /* reward_weights */
+  float too_far_dist, bad_pose_dist, bad_quat_dist;
+  float ctrl_cost_weight, ctrl_diff_cost_weight, energy_cost_weight;
+  float pos_reward_weight, quat_reward_weight, joint_reward_weight;
+  float angvel_reward_weight, bodypos_reward_weight, endeff_reward_weight;
+  float healthy_z_min, healthy_z_max;
+  float pos_reward_exp_scale, quat_reward_exp_scale, joint_reward_exp_scale;
+  float angvel_reward_exp_scale, bodypos_reward_exp_scale, endeff_reward_exp_scale;
+  float penalty_pos_distance_scale[3];
+  int32_t var_window_size;
+  float var_coeff, jerk_coeff;
+  /* walker index tables: MODEL ids exactly as mj_name2id returns them (the off-by-one between
+   * `data.xpos[1:]` and these ids, and the clamp of id 67, are reproduced inside the step) */
+  int32_t n_joint_idxs, n_body_idxs, n_endeff_idxs;
+  int32_t joint_idxs[TMJX_MAX_IDX];
+  int32_t body_idxs[TMJX_MAX_IDX];
+  int32_t endeff_idxs[TMJX_MAX_IDX];
+  int32_t torso_idx;
+  /* named bindings used by _get_proprioception / _get_appendages_pos (single_clip_tracking.py:322-354) */
+  int32_t torso_body_id;
+  int32_t n_appendages;
+  int32_t appendage_body_ids[8];
+} TmjxTaskConfig;
+
+/* Per-env state carried between calls (caller-owned device buffers, all `[n_env, dim]`).
+ * pipeline_state subset of mjx.Data that is persistent: qpos, qvel, act, time, qacc_warmstart, plus the
+ * derived quantities the reference reads one call later (they are "stale by one substep" in the reference
+ * too because mjx.step integrates after forward): xpos, xquat, qfrc_actuator. */
+typedef struct TmjxState {
+  float* qpos;            /* [n, nq]  */
+  float* qvel;            /* [n, nv]  */
+  float* act;             /* [n, na]  */
+  float* time;            /* [n]      */
+  float* qacc_warmstart;  /* [n, nv]  */
+  float* xpos;            /* [n, nbody, 3]  derived, written by forward/step */
+  float* xquat;           /* [n, nbody, 4]  derived, written by forward/step */
+  float* qfrc_actuator;   /* [n, nv]        derived, written by forward/step */
+  /* info */
+  int32_t* clip_idx;      /* [n] */
+  int32_t* start_frame;   /* [n] */
+  int32_t* buffer_index;  /* [n] */
+  float* prev_ctrl;       /* [n, nu] */
+  float* action_buffer;   /* [n, var_window_size, nu] */
+  /* wrapper state (EpisodeWrapper + AutoResetWrapperTracking); may be NULL when flags do not ask for it */
+  float* steps;           /* [n] */
+  float* truncation;      /* [n] */
+  float* first_qpos;      /* [n, nq] snapshot taken by tmjx_forward with TMJX_F_SNAPSHOT */
+  float* first_qvel;      /* [n, nv] */
+  float* first_act;       /* [n, na] */
+  float* first_time;      /* [n] */
+  float* first_qacc_warmstart; /* [n, nv] */
+  float* first_xpos;      /* [n, nbody, 3] */
+  float* first_xquat;     /* [n, nbody, 4] */
+  float* first_qfrc_actuator; /* [n, nv] */
+  float* first_obs;       /* [n, obs] */
+  float* first_prev_ctrl; /* [n, nu] */
+} TmjxState;
+
+typedef struct TmjxOut {
+  float* obs;             /* [n, obs_size]  reference_obs ‖ proprioceptive_obs */
+  float* reward;          /* [n] */
+  float* done;            /* [n] fp32 0/1 like the reference; read as the PREVIOUS done with TMJX_F_AUTORESET */
+  float* metrics;         /* [n, TMJX_N_METRICS] */
+  int32_t* cur_frame;     /* [n] */
+  /* optional debug taps for parity tests (NULL = skip) */
+  float* dbg_qacc;        /* [n, nv]   solver output of the last substep */
+  float* dbg_qacc_smooth; /* [n, nv] */
+  float* dbg_qfrc_bias;   /* [n, nv] */
+  float* dbg_qfrc_constraint; /* [n, nv] */
+  float* dbg_contact_dist;/* [n, ncon] */
+  float* dbg_efc_force;   /* [n, nefc] */
+  float* dbg_qM;          /* [n, nv, nv] dense symmetric */
+  float* dbg_subtree_com; /* [n, 3] of the walker tree root */
+} TmjxOut;
+
+/* step flags */
+#define TMJX_F_AUTORESET   1u  /* fuse EpisodeWrapper + AutoResetWrapperTracking (wrappers.py:288-310) */
+#define TMJX_F_SNAPSHOT    2u  /* tmjx_forward: also store first_* (wrappers.py:281-286) */
+
+typedef struct TmjxModel TmjxModel;
+typedef struct TmjxClips TmjxClips;
+
+/* sizes derived from the model + task (for buffer allocation by the caller) */
+typedef struct TmjxDims {
+  int32_t nq, nv, nu, na, nbody, njnt, ncon, nefc;
+  int32_t obs_size, reference_obs_size, proprioceptive_obs_size;
+  int32_t var_window_size, n_metrics;
+  int32_t smem_bytes_per_env, envs_per_block, threads_per_env;
+} TmjxDims;
+
+int tmjx_abi_version(void);
+const char* tmjx_last_error(void);
+
+/* `blob` = model-constant table produced by track-mjx_b200/model_blob.py (host memory). */
+int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg, int device, TmjxModel** out);
+void tmjx_model_destroy(TmjxModel* m);
+int tmjx_model_dims(const TmjxModel* m, TmjxDims* out);
+
+/* Reference clips: HOST pointers to the eight ReferenceClip fields (io/load.py:16-38), each
+ * `[n_clips, clip_len, d]` fp32 row-major. The hot subset is packed into one device table. */
+int tmjx_clips_create(const TmjxModel* m, const float* position, const float* quaternion, const float* joints,
+                      const float* body_positions, const float* velocity, const float* angular_velocity,
+                      const float* joints_velocity, const float* body_quaternions, int n_clips, int clip_len,
+                      int n_ref_bodies, TmjxClips** out);
+void tmjx_clips_destroy(TmjxClips* c);
+size_t tmjx_clips_device_bytes(const TmjxClips* c);
+
+/* reset path: qpos/qvel/(act,time,warmstart are zeroed) given -> mjx.forward -> obs; zero reward/done/metrics,
+ * zero action_buffer/buffer_index (single_clip_tracking.py:163-205). */
+int tmjx_forward(const TmjxModel* m, const TmjxClips* c, TmjxState* s, TmjxOut* o, int n_env, unsigned flags,
+                 void* stream);
+
+/* one control step (single_clip_tracking.py:207-320), optionally with the wrappers fused. */
+int tmjx_step(const TmjxModel* m, const TmjxClips* c, const float* action, TmjxState* s, TmjxOut* o, int n_env,
+              unsigned flags, void* stream);
+
+/* FP32 FMA-throughput microbenchmark used as the roofline denominator (returns TFLOP/s, <0 on error). */
+double tmjx_fp32_peak_tflops(int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMJX_H_ */

@@ -1,0 +1,1532 @@
+/*
+ * tmjx_step.cu — sm_100a kernels + C ABI (include/tmjx.h) for the batched rodent-tracking env step.
+ *
+ * One WARP per environment, all per-env state staged in shared memory / registers, one launch per control
+ * step: `physics_steps_per_control_step` x (forward dynamics + constraint solve + Euler) followed by the
+ * tracking reward / termination / observation epilogue.  Replaces, for this path,
+ *   SingleClipTracking.step / reset_from_clip   reference track_mjx/environment/task/single_clip_tracking.py:121-320
+ *   compute_tracking_rewards                     reference track_mjx/environment/task/reward.py:359-485
+ *   BaseWalker.compute_local_*                   reference track_mjx/environment/walker/base.py:170-258
+ *   brax PipelineEnv.pipeline_step -> mjx.step   (upstream mujoco-mjx 3.3.2; called at single_clip_tracking.py:219)
+ *
+ * B200 design notes (DESIGN.md has the full story):
+ *   - the path is FP32-latency bound, not HBM bound (15 KB of HBM traffic vs ~4 MFLOP per env step), so the
+ *     design goal is resident environments per SM: the per-env shared-memory slice is ~17 KB by aliasing the
+ *     smooth-dynamics transients with the two sparse LDL factors, and nv- / constraint-row vectors live in
+ *     registers (lane l owns dofs l, l+32, l+64 and the 4 pyramid rows of contact l + 3 joint-limit rows);
+ *   - structure-exploiting instead of MJX's dense algebra: sparse L^T D L of the joint-space inertia with the
+ *     damping-augmented factor (Euler) built in the same sweep, scatter-form triangular solves without
+ *     shuffles, and a Jacobian-free constraint operator (contact-point velocities from per-body spatial
+ *     velocity sums; forces mapped back as wrenches about the subtree COM);
+ *   - tree passes are level-parallel with deterministic child gathers (no atomics => bitwise reproducible,
+ *     independent of grid size, so sharding over GPUs cannot change per-env results).
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tmjx_tables.h"
+
+namespace tmjx {
+
+#define FULLMASK 0xffffffffu
+constexpr float kMinVal = 1e-15f;
+
+// ---------------------------------------------------------------------------------------------- device math
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  const float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void rot(const float* v, const float* q, float* o) {  // mjx math.rotate
+  const float s = q[0];
+  const float* u = q + 1;
+  float c[3];
+  cross3(u, v, c);
+  const float uv = dot3(u, v), uu = dot3(u, u), k = s * s - uu;
+  const float r0 = 2.f * (uv * u[0]) + k * v[0] + 2.f * s * c[0];
+  const float r1 = 2.f * (uv * u[1]) + k * v[1] + 2.f * s * c[1];
+  const float r2 = 2.f * (uv * u[2]) + k * v[2] + 2.f * s * c[2];
+  o[0] = r0; o[1] = r1; o[2] = r2;
+}
+__device__ __forceinline__ void qmul(const float* a, const float* b, float* o) {
+  const float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  const float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  const float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  const float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+__device__ __forceinline__ void q2mat(const float* q, float* m) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2.f * (x * y - w * z); m[2] = 2.f * (x * z + w * y);
+  m[3] = 2.f * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2.f * (y * z - w * x);
+  m[6] = 2.f * (x * z - w * y); m[7] = 2.f * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ float normalize3(float* x) {  // math.normalize_with_norm
+  const float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const float d = n + (n == 0.f ? 1e-6f : 0.f);
+  x[0] = x[0] / d; x[1] = x[1] / d; x[2] = x[2] / d;
+  return n;
+}
+__device__ __forceinline__ void normalize4(float* x) {
+  const float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  const float d = n + (n == 0.f ? 1e-6f : 0.f);
+  x[0] = x[0] / d; x[1] = x[1] / d; x[2] = x[2] / d; x[3] = x[3] / d;
+}
+__device__ __forceinline__ void inert_mul(const float* i, const float* v, float* o) {  // math.inert_mul
+  float c1[3], c2[3];
+  cross3(i + 6, v + 3, c1);
+  cross3(i + 6, v, c2);
+  const float r0 = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] + c1[0];
+  const float r1 = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + c1[1];
+  const float r2 = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] + c1[2];
+  const float r3 = i[9] * v[3] - c2[0], r4 = i[9] * v[4] - c2[1], r5 = i[9] * v[5] - c2[2];
+  o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5;
+}
+__device__ __forceinline__ void motion_cross(const float* u, const float* v, float* o) {
+  float a[3], b[3], c[3];
+  cross3(u, v, a);
+  cross3(u + 3, v, b);
+  cross3(u, v + 3, c);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = b[0] + c[0]; o[4] = b[1] + c[1]; o[5] = b[2] + c[2];
+}
+__device__ __forceinline__ void motion_cross_force(const float* v, const float* f, float* o) {
+  float a[3], b[3], c[3];
+  cross3(v, f, a);
+  cross3(v + 3, f + 3, b);
+  cross3(v, f + 3, c);
+  o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; o[3] = c[0]; o[4] = c[1]; o[5] = c[2];
+}
+// constraint._kbi impedance for |pos| given the pre-digested solimp (par = dmin dmax width mid power)
+__device__ __forceinline__ float impedance(const float* par, float pos) {
+  const float dmin = par[0], dmax = par[1], width = par[2], mid = par[3], power = par[4];
+  const float x = fabsf(pos) / width;
+  float a, b;
+  if (power == 2.f) {
+    a = (1.f / mid) * (x * x);
+    b = 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
+  } else {
+    a = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+    b = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  }
+  const float y = x < mid ? a : b;
+  float imp = dmin + y * (dmax - dmin);
+  imp = fminf(fmaxf(imp, dmin), dmax);
+  if (x > 1.f) imp = dmax;
+  return imp;
+}
+
+// ---------------------------------------------------------------------------------------------- per-warp context
+struct Warp {
+  const DevModel& m;
+  float* s;  // this environment's shared-memory slice
+  int lane;
+  __device__ __forceinline__ float* at(int off) const { return s + off; }
+};
+
+// registers owned by a lane across the solver
+struct Rows {
+  float D[kRowSlots], aref[kRowSlots];
+  float mu;          // friction of contact `lane`
+  bool cact;         // contact `lane` penetrating (J rows non-zero)
+  float lsign[kLimSlots];  // +-1 / 0 sign of the limit Jacobian entry
+};
+
+// ---- nv-vector helpers: lane l owns dofs l + 32 q
+__device__ __forceinline__ void vput(const Warp& w, float* dst, const float v[kNvSlots]) {
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { const int d = w.lane + 32 * q; if (d < w.m.nv) dst[d] = v[q]; }
+}
+__device__ __forceinline__ void vget(const Warp& w, const float* src, float v[kNvSlots]) {
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { const int d = w.lane + 32 * q; v[q] = d < w.m.nv ? src[d] : 0.f; }
+}
+__device__ __forceinline__ float vdot(const float a[kNvSlots], const float b[kNvSlots]) {
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) s += a[q] * b[q];
+  return wsum(s);
+}
+
+// ---------------------------------------------------------------------------------------------- smooth dynamics
+// smooth.kinematics: level-parallel over bodies
+__device__ void kinematics(const Warp& w) {
+  const DevModel& m = w.m;
+  float* qpos = w.at(m.o_qpos);
+  float* xpos = w.at(m.o_xpos);
+  float* xquat = w.at(m.o_xquat);
+  float* xipos = w.at(m.o_big + m.a_xipos);
+  float* anchor = w.at(m.o_big + m.a_anchor);
+  float* axis = w.at(m.o_big + m.a_axis);
+  for (int lv = 0; lv < m.nlevel; ++lv) {
+    const int beg = m.lvl_start[lv], end = m.lvl_start[lv + 1];
+    for (int idx = beg + w.lane; idx < end; idx += 32) {
+      const int b = m.lvl_body[idx];
+      float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
+      if (b > 0) {
+        const int p = m.body_parent[b];
+        float t[3];
+        rot(m.body_pos + b * 3, xquat + p * 4, t);
+        pos[0] = xpos[p * 3] + t[0]; pos[1] = xpos[p * 3 + 1] + t[1]; pos[2] = xpos[p * 3 + 2] + t[2];
+        qmul(xquat + p * 4, m.body_quat + b * 4, quat);
+        const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
+        for (int jj = 0; jj < jn; ++jj) {
+          const int j = ja + jj, qa = m.jnt_qposadr[j];
+          if (m.jnt_type[j] == kJntFree) {
+            anchor[j * 3] = qpos[qa]; anchor[j * 3 + 1] = qpos[qa + 1]; anchor[j * 3 + 2] = qpos[qa + 2];
+            axis[j * 3] = 0.f; axis[j * 3 + 1] = 0.f; axis[j * 3 + 2] = 1.f;
+            pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
+            quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
+            normalize4(quat);
+            qpos[qa + 3] = quat[0]; qpos[qa + 4] = quat[1]; qpos[qa + 5] = quat[2]; qpos[qa + 6] = quat[3];
+          } else {
+            float jp[3] = {m.jnt_pos[j * 3], m.jnt_pos[j * 3 + 1], m.jnt_pos[j * 3 + 2]};
+            float ja3[3] = {m.jnt_axis[j * 3], m.jnt_axis[j * 3 + 1], m.jnt_axis[j * 3 + 2]};
+            float an[3];
+            rot(jp, quat, t);
+            an[0] = t[0] + pos[0]; an[1] = t[1] + pos[1]; an[2] = t[2] + pos[2];
+            anchor[j * 3] = an[0]; anchor[j * 3 + 1] = an[1]; anchor[j * 3 + 2] = an[2];
+            rot(ja3, quat, t);
+            axis[j * 3] = t[0]; axis[j * 3 + 1] = t[1]; axis[j * 3 + 2] = t[2];
+            float sn, cs;
+            sincosf((qpos[qa] - m.jnt_qpos0[j]) * 0.5f, &sn, &cs);
+            const float ql[4] = {cs, ja3[0] * sn, ja3[1] * sn, ja3[2] * sn};
+            float q2[4];
+            qmul(quat, ql, q2);
+            quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+            rot(jp, quat, t);
+            pos[0] = an[0] - t[0]; pos[1] = an[1] - t[1]; pos[2] = an[2] - t[2];
+          }
+        }
+      }
+      xpos[b * 3] = pos[0]; xpos[b * 3 + 1] = pos[1]; xpos[b * 3 + 2] = pos[2];
+      xquat[b * 4] = quat[0]; xquat[b * 4 + 1] = quat[1]; xquat[b * 4 + 2] = quat[2]; xquat[b * 4 + 3] = quat[3];
+      float t[3];
+      rot(m.body_ipos + b * 3, quat, t);
+      xipos[b * 3] = pos[0] + t[0]; xipos[b * 3 + 1] = pos[1] + t[1]; xipos[b * 3 + 2] = pos[2] + t[2];
+    }
+    __syncwarp();
+  }
+}
+
+// smooth.com_pos: COM of the moving tree (warp reduction), cinert per body, cdof per dof
+__device__ void com_pos(const Warp& w, float com[3]) {
+  const DevModel& m = w.m;
+  const float* xquat = w.at(m.o_xquat);
+  const float* xipos = w.at(m.o_big + m.a_xipos);
+  const float* anchor = w.at(m.o_big + m.a_anchor);
+  const float* axis = w.at(m.o_big + m.a_axis);
+  const float* qpos = w.at(m.o_qpos);
+  float* cin = w.at(m.o_cin);
+  float* cdof = w.at(m.o_cdof);
+  float px = 0.f, py = 0.f, pz = 0.f;
+  for (int b = w.lane; b < m.nbody; b += 32) {
+    const float mt = m.body_tree_mass[b];
+    px += xipos[b * 3] * mt; py += xipos[b * 3 + 1] * mt; pz += xipos[b * 3 + 2] * mt;
+  }
+  com[0] = wsum(px) / m.tree_mass; com[1] = wsum(py) / m.tree_mass; com[2] = wsum(pz) / m.tree_mass;
+  for (int b = w.lane; b < m.nbody; b += 32) {
+    float q[4], R[9];
+    qmul(xquat + b * 4, m.body_iquat + b * 4, q);
+    q2mat(q, R);
+    const float I0 = m.body_inertia[b * 3], I1 = m.body_inertia[b * 3 + 1], I2 = m.body_inertia[b * 3 + 2], ms = m.body_mass[b];
+    const float off[3] = {xipos[b * 3] - com[0], xipos[b * 3 + 1] - com[1], xipos[b * 3 + 2] - com[2]};
+    const float oo = dot3(off, off);
+    float* ci = cin + b * 10;
+#define INRC(r, c) (R[r * 3] * I0 * R[c * 3] + R[r * 3 + 1] * I1 * R[c * 3 + 1] + R[r * 3 + 2] * I2 * R[c * 3 + 2])
+    ci[0] = INRC(0, 0) + (oo - off[0] * off[0]) * ms;
+    ci[1] = INRC(1, 1) + (oo - off[1] * off[1]) * ms;
+    ci[2] = INRC(2, 2) + (oo - off[2] * off[2]) * ms;
+    ci[3] = INRC(0, 1) + (0.f - off[0] * off[1]) * ms;
+    ci[4] = INRC(0, 2) + (0.f - off[0] * off[2]) * ms;
+    ci[5] = INRC(1, 2) + (0.f - off[1] * off[2]) * ms;
+#undef INRC
+    ci[6] = off[0] * ms; ci[7] = off[1] * ms; ci[8] = off[2] * ms; ci[9] = ms;
+  }
+  for (int d = w.lane; d < m.nv; d += 32) {
+    const int j = m.dof_jnt[d];
+    float* cd = cdof + d * 6;
+    const float off[3] = {com[0] - anchor[j * 3], com[1] - anchor[j * 3 + 1], com[2] - anchor[j * 3 + 2]};
+    if (m.jnt_type[j] == kJntFree) {
+      const int r = d - m.jnt_dofadr[j];
+      if (r < 3) {
+        cd[0] = cd[1] = cd[2] = 0.f;
+        cd[3] = r == 0 ? 1.f : 0.f; cd[4] = r == 1 ? 1.f : 0.f; cd[5] = r == 2 ? 1.f : 0.f;
+      } else {
+        float R[9];
+        q2mat(xquat + m.jnt_body[j] * 4, R);
+        const int c = r - 3;
+        const float a[3] = {R[c], R[3 + c], R[6 + c]};
+        cd[0] = a[0]; cd[1] = a[1]; cd[2] = a[2];
+        cross3(a, off, cd + 3);
+      }
+    } else {
+      const float a[3] = {axis[j * 3], axis[j * 3 + 1], axis[j * 3 + 2]};
+      cd[0] = a[0]; cd[1] = a[1]; cd[2] = a[2];
+      cross3(a, off, cd + 3);
+    }
+  }
+  (void)qpos;
+  __syncwarp();
+}
+
+// smooth.com_vel + the cacc scan of smooth.rne, one level-parallel sweep; then local cfrc, leaf-to-root gather,
+// qfrc_bias per dof (returned in registers)
+__device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
+  const DevModel& m = w.m;
+  const float* qvel = w.at(m.o_qvel);
+  const float* cdof = w.at(m.o_cdof);
+  const float* cin = w.at(m.o_cin);
+  float* cvel = w.at(m.o_big + m.a_cvel);
+  float* cdd = w.at(m.o_big + m.a_cdofdot);
+  float* cacc = w.at(m.o_big + m.a_cacc);
+  if (w.lane < 6) { cvel[w.lane] = 0.f; cacc[w.lane] = w.lane < 3 ? 0.f : -m.gravity[w.lane - 3]; }
+  __syncwarp();
+  for (int lv = 1; lv < m.nlevel; ++lv) {
+    const int beg = m.lvl_start[lv], end = m.lvl_start[lv + 1];
+    for (int idx = beg + w.lane; idx < end; idx += 32) {
+      const int b = m.lvl_body[idx], p = m.body_parent[b];
+      float cv[6], ca[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { cv[k] = cvel[p * 6 + k]; ca[k] = cacc[p * 6 + k]; }
+      const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = ja + jj, da = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == kJntFree) {
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { cv[k] += cdof[(da + r) * 6 + k] * qvel[da + r]; cdd[(da + r) * 6 + k] = 0.f; }
+          for (int r = 3; r < 6; ++r) {
+            float t[6];
+            motion_cross(cv, cdof + (da + r) * 6, t);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cdd[(da + r) * 6 + k] = t[k];
+          }
+          for (int r = 3; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cv[k] += cdof[(da + r) * 6 + k] * qvel[da + r];
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ca[k] += cdd[(da + r) * 6 + k] * qvel[da + r];
+        } else {
+          float t[6];
+          motion_cross(cv, cdof + da * 6, t);
+          const float v = qvel[da];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { cdd[da * 6 + k] = t[k]; cv[k] += cdof[da * 6 + k] * v; ca[k] += t[k] * v; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { cvel[b * 6 + k] = cv[k]; cacc[b * 6 + k] = ca[k]; }
+    }
+    __syncwarp();
+  }
+  // local cfrc (in place of cacc)
+  for (int b = w.lane; b < m.nbody; b += 32) {
+    float f1[6], f2[6], f3[6];
+    inert_mul(cin + b * 10, cacc + b * 6, f1);
+    inert_mul(cin + b * 10, cvel + b * 6, f2);
+    motion_cross_force(cvel + b * 6, f2, f3);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = f1[k] + f3[k];
+  }
+  __syncwarp();
+  for (int lv = m.nlevel - 2; lv >= 1; --lv) {  // deterministic child gather
+    const int beg = m.lvl_start[lv], n = (m.lvl_start[lv + 1] - beg) * 6;
+    for (int t = w.lane; t < n; t += 32) {
+      const int b = m.lvl_body[beg + t / 6], k = t % 6;
+      float acc = cacc[b * 6 + k];
+      for (int c = m.child_start[b]; c < m.child_start[b + 1]; ++c) acc += cacc[m.child[c] * 6 + k];
+      cacc[b * 6 + k] = acc;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    float acc = 0.f;
+    if (d < m.nv) {
+      const float* cf = cacc + m.dof_body[d] * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc += cdof[d * 6 + k] * cf[k];
+    }
+    bias[q] = acc;
+  }
+}
+
+// passive.passive + forward.fwd_actuation; returns qfrc_actuator and qfrc_smooth in registers
+__device__ void passive_actuation(const Warp& w, const float bias[kNvSlots], float qfa[kNvSlots], float qfs[kNvSlots],
+                                  float actdot[2]) {
+  const DevModel& m = w.m;
+  const float* qpos = w.at(m.o_qpos);
+  const float* qvel = w.at(m.o_qvel);
+  const float* act = w.at(m.o_act);
+  const float* ctrl = w.at(m.o_ctrl);
+  float* force = w.at(m.o_big + m.a_force);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int u = w.lane + 32 * k;
+    actdot[k] = 0.f;
+    if (u < m.nu) {
+      const int fl = m.act_flags[u];
+      const float c = ctrl[u];
+      float ca = c;
+      if (fl & 2) { actdot[k] = (c - act[u]) / m.act_dyn_inv[u]; ca = act[u]; }
+      float f = m.act_gain[u] * ca;
+      if (fl & 4) {
+        float len = 0.f, vel = 0.f;
+        for (int e = m.act_mom_start[u]; e < m.act_mom_start[u + 1]; ++e) {
+          const int d = m.act_mom_dof[e];
+          len += m.act_mom_coef[e] * qpos[d + 1];
+          vel += m.act_mom_coef[e] * qvel[d];
+        }
+        f += m.act_bias[u * 3] + m.act_bias[u * 3 + 1] * len + m.act_bias[u * 3 + 2] * vel;
+      }
+      if (fl & 8) f = fminf(fmaxf(f, m.act_force_lo[u]), m.act_force_hi[u]);
+      force[u] = f;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    float a = 0.f, pas = 0.f;
+    if (d < m.nv) {
+      for (int e = m.dof_act_start[d]; e < m.dof_act_start[d + 1]; ++e) a += m.dof_act_coef[e] * force[m.dof_act_id[e]];
+      pas = -m.dof_damping[d] * qvel[d];
+      const int qa = m.dof_qadr[d];
+      if (qa >= 0) { const int j = m.dof_jnt[d]; pas += -m.jnt_stiffness[j] * (qpos[qa] - m.jnt_springref[j]); }
+    }
+    qfa[q] = a;
+    qfs[q] = pas - bias[q] + a;
+  }
+}
+
+// smooth.crb + support.make_m into the sparse rows of L1, then the damping-augmented copy L2, then both
+// L^T D L factorisations in one sweep (smooth.factor_m, and the one forward.euler would do later)
+__device__ void crb_factor(const Warp& w) {
+  const DevModel& m = w.m;
+  float* crb = w.at(m.o_cin);
+  const float* cdof = w.at(m.o_cdof);
+  float* L1 = w.at(m.o_big);
+  float* L2 = w.at(m.o_big + m.nMpad);
+  float* f = L2;  // M-build scratch, dead before L2 is written
+  for (int lv = m.nlevel - 2; lv >= 1; --lv) {
+    const int beg = m.lvl_start[lv], n = (m.lvl_start[lv + 1] - beg) * 10;
+    for (int t = w.lane; t < n; t += 32) {
+      const int b = m.lvl_body[beg + t / 10], k = t % 10;
+      float acc = crb[b * 10 + k];
+      for (int c = m.child_start[b]; c < m.child_start[b + 1]; ++c) acc += crb[m.child[c] * 10 + k];
+      crb[b * 10 + k] = acc;
+    }
+    __syncwarp();
+  }
+  for (int d = w.lane; d < m.nv; d += 32) {
+    float t[6];
+    inert_mul(crb + m.dof_body[d] * 10, cdof + d * 6, t);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) f[d * 6 + k] = t[k];
+  }
+  __syncwarp();
+  for (int e = w.lane; e < m.nM; e += 32) {
+    const int i = m.m_row[e], j = m.m_col[e];
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v += f[i * 6 + k] * cdof[j * 6 + k];
+    if (i == j) v += m.dof_armature[i];
+    L1[e] = v;
+  }
+  __syncwarp();  // f (aliasing L2) is dead from here
+  for (int e = w.lane; e < m.nM; e += 32) {
+    const int i = m.m_row[e];
+    L2[e] = (i == m.m_col[e]) ? L1[e] + m.dt * m.dof_damping[i] : L1[e];
+  }
+  __syncwarp();
+  float* sD = w.at(m.o_cin + m.c_sD);
+  for (int k = m.nv - 1; k >= 0; --k) {
+    const int adr = m.dof_madr[k], c = m.dof_depth[k];
+    const float d1 = L1[adr], d2 = L2[adr];
+    const float inv1 = 1.f / d1, inv2 = 1.f / d2;
+    const int npair = c * (c + 1) / 2;
+    for (int p = w.lane; p < npair; p += 32) {
+      const int a = m.tri_a[p] + 1, b = m.tri_b[p] + 1;
+      const int tgt = m.dof_madr[m.m_anc[adr + a]] + (b - a);
+      L1[tgt] -= L1[adr + a] * L1[adr + b] * inv1;
+      L2[tgt] -= L2[adr + a] * L2[adr + b] * inv2;
+    }
+    __syncwarp();
+    for (int a = 1 + w.lane; a <= c; a += 32) { L1[adr + a] *= inv1; L2[adr + a] *= inv2; }
+    if (w.lane == 0) { L1[adr] = inv1; L2[adr] = inv2; sD[k] = d1; }
+    __syncwarp();
+  }
+}
+
+// x <- (L^T D L)^-1 x in shared memory; scatter form (mj_solveLD order), no shuffles
+__device__ void solve_ld(const Warp& w, const float* L, float* x) {
+  const DevModel& m = w.m;
+  for (int i = m.nv - 1; i >= 0; --i) {
+    const int adr = m.dof_madr[i], c = m.dof_depth[i];
+    const float xi = x[i];
+    for (int a = 1 + w.lane; a <= c; a += 32) x[m.m_anc[adr + a]] -= L[adr + a] * xi;
+    __syncwarp();
+  }
+  for (int d = w.lane; d < m.nv; d += 32) x[d] *= L[m.dof_madr[d]];
+  __syncwarp();
+  for (int j = 0; j < m.nv; ++j) {
+    const float xj = x[j];
+    for (int t = m.desc_start[j] + w.lane; t < m.desc_start[j + 1]; t += 32) x[m.desc_dof[t]] -= L[m.desc_off[t]] * xj;
+    __syncwarp();
+  }
+}
+
+// out = M x with M = L1^T D L1; x in shared memory (sx), uses sy as scratch
+__device__ void mul_m(const Warp& w, const float* x, float out[kNvSlots]) {
+  const DevModel& m = w.m;
+  const float* L = w.at(m.o_big);
+  const float* sD = w.at(m.o_cin + m.c_sD);
+  float* y = w.at(m.o_cin + m.c_sy);
+  for (int d = w.lane; d < m.nv; d += 32) {
+    const int adr = m.dof_madr[d], c = m.dof_depth[d];
+    float acc = x[d];
+    for (int a = 1; a <= c; ++a) acc += L[adr + a] * x[m.m_anc[adr + a]];
+    y[d] = acc * sD[d];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    float acc = 0.f;
+    if (d < m.nv) {
+      acc = y[d];
+      for (int t = m.desc_start[d]; t < m.desc_start[d + 1]; ++t) acc += L[m.desc_off[t]] * y[m.desc_dof[t]];
+    }
+    out[q] = acc;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- constraints
+// jv = J x for the rows this lane owns; x in shared memory
+__device__ void apply_J(const Warp& w, const Rows& r, const float* x, float jv[kRowSlots]) {
+  const DevModel& m = w.m;
+  const float* cdof = w.at(m.o_cdof);
+  float* sV = w.at(m.o_cin + m.c_sV);
+  for (int t = w.lane; t < m.ncb * 6; t += 32) {
+    const int cb = t / 6, k = t % 6;
+    float acc = 0.f;
+    for (int e = m.cb_chain_start[cb]; e < m.cb_chain_start[cb + 1]; ++e) { const int d = m.cb_chain_dof[e]; acc += cdof[d * 6 + k] * x[d]; }
+    sV[t] = acc;
+  }
+  __syncwarp();
+  jv[0] = jv[1] = jv[2] = jv[3] = 0.f;
+  if (w.lane < m.ncon && r.cact) {
+    const float* V = sV + m.con_cb[w.lane] * 6;
+    const float* off = w.at(m.o_cin + m.c_off) + w.lane * 3;
+    const float* t1 = w.at(m.o_cin + m.c_t1) + w.lane * 3;
+    float vel[3], t2[3];
+    cross3(V, off, vel);
+    vel[0] += V[3]; vel[1] += V[4]; vel[2] += V[5];
+    cross3(m.plane_n, t1, t2);
+    const float jn = dot3(m.plane_n, vel), j1 = dot3(t1, vel), j2 = dot3(t2, vel);
+    jv[0] = jn + j1 * r.mu; jv[1] = jn - j1 * r.mu; jv[2] = jn + j2 * r.mu; jv[3] = jn - j2 * r.mu;
+  }
+#pragma unroll
+  for (int q = 0; q < kLimSlots; ++q) {
+    const int l = w.lane + 32 * q;
+    jv[4 + q] = l < m.nlimit ? r.lsign[q] * x[m.lim_dof[l]] : 0.f;
+  }
+  __syncwarp();
+}
+
+// out = J^T f for the dofs this lane owns
+__device__ void apply_JT(const Warp& w, const Rows& r, const float f[kRowSlots], float out[kNvSlots]) {
+  const DevModel& m = w.m;
+  const float* cdof = w.at(m.o_cdof);
+  float* sW = w.at(m.o_cin + m.c_sW);
+  float* sWb = w.at(m.o_cin + m.c_sWb);
+  float* lf = w.at(m.o_cin + m.c_lf);
+  if (w.lane < m.ncon) {
+    const float* off = w.at(m.o_cin + m.c_off) + w.lane * 3;
+    const float* t1 = w.at(m.o_cin + m.c_t1) + w.lane * 3;
+    float t2[3], fw[3], tau[3];
+    cross3(m.plane_n, t1, t2);
+    const float fn = f[0] + f[1] + f[2] + f[3], f1 = (f[0] - f[1]) * r.mu, f2 = (f[2] - f[3]) * r.mu;
+    fw[0] = m.plane_n[0] * fn + t1[0] * f1 + t2[0] * f2;
+    fw[1] = m.plane_n[1] * fn + t1[1] * f1 + t2[1] * f2;
+    fw[2] = m.plane_n[2] * fn + t1[2] * f1 + t2[2] * f2;
+    cross3(off, fw, tau);
+    float* o = sW + w.lane * 6;
+    o[0] = tau[0]; o[1] = tau[1]; o[2] = tau[2]; o[3] = fw[0]; o[4] = fw[1]; o[5] = fw[2];
+  }
+#pragma unroll
+  for (int q = 0; q < kLimSlots; ++q) {
+    const int l = w.lane + 32 * q;
+    if (l < m.nlimit) lf[l] = r.lsign[q] * f[4 + q];
+  }
+  __syncwarp();
+  for (int t = w.lane; t < m.ncb * 6; t += 32) {
+    const int cb = t / 6, k = t % 6;
+    float acc = 0.f;
+    for (int e = m.cb_con_start[cb]; e < m.cb_con_start[cb + 1]; ++e) acc += sW[m.cb_con[e] * 6 + k];
+    sWb[t] = acc;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    float acc = 0.f;
+    if (d < m.nv) {
+      for (int e = m.dof_cb_start[d]; e < m.dof_cb_start[d + 1]; ++e) {
+        const float* W = sWb + m.dof_cb[e] * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc += cdof[d * 6 + k] * W[k];
+      }
+      const int l = m.dof_limit[d];
+      if (l >= 0) acc += lf[l];
+    }
+    out[q] = acc;
+  }
+  __syncwarp();
+}
+
+// collision_primitive.plane_{sphere,capsule,ellipsoid} + constraint.make_constraint (limits + pyramidal contacts)
+__device__ void make_constraint(const Warp& w, const float com[3], Rows& r, float* dbg_dist) {
+  const DevModel& m = w.m;
+  const float* xpos = w.at(m.o_xpos);
+  const float* xquat = w.at(m.o_xquat);
+  const float* qpos = w.at(m.o_qpos);
+  const float* n = m.plane_n;
+  float cpos = 0.f;  // dist - includemargin of contact `lane`
+  r.mu = 0.f; r.cact = false;
+  float cD = 0.f, ck = 0.f, cb_ = 0.f, cimp = 0.f;
+  if (w.lane < m.ncon) {
+    const int c = w.lane, g = m.con_geom[c], b = m.cg_body[g], type = m.cg_type[g];
+    const float* par = m.con_par + c * 12;
+    float gpos[3], gq[4], t[3], pos[3], t1[3], dist;
+    rot(m.cg_pos + g * 3, xquat + b * 4, t);
+    gpos[0] = xpos[b * 3] + t[0]; gpos[1] = xpos[b * 3 + 1] + t[1]; gpos[2] = xpos[b * 3 + 2] + t[2];
+    qmul(xquat + b * 4, m.cg_quat + g * 4, gq);
+    const float sz0 = m.cg_size[g * 3], sz1 = m.cg_size[g * 3 + 1], sz2 = m.cg_size[g * 3 + 2];
+    float R[9];
+    q2mat(gq, R);
+    if (type == kGeomEllipsoid) {
+      float sv[3] = {(R[0] * n[0] + R[3] * n[1] + R[6] * n[2]) * sz0, (R[1] * n[0] + R[4] * n[1] + R[7] * n[2]) * sz1,
+                     (R[2] * n[0] + R[5] * n[1] + R[8] * n[2]) * sz2};
+      normalize3(sv);
+      sv[0] = -sv[0] * sz0; sv[1] = -sv[1] * sz1; sv[2] = -sv[2] * sz2;
+      pos[0] = gpos[0] + R[0] * sv[0] + R[1] * sv[1] + R[2] * sv[2];
+      pos[1] = gpos[1] + R[3] * sv[0] + R[4] * sv[1] + R[5] * sv[2];
+      pos[2] = gpos[2] + R[6] * sv[0] + R[7] * sv[1] + R[8] * sv[2];
+      const float dl[3] = {pos[0] - m.plane_pos[0], pos[1] - m.plane_pos[1], pos[2] - m.plane_pos[2]};
+      dist = dot3(n, dl);
+      pos[0] = pos[0] - n[0] * dist * 0.5f; pos[1] = pos[1] - n[1] * dist * 0.5f; pos[2] = pos[2] - n[2] * dist * 0.5f;
+    } else {
+      float sp[3] = {gpos[0], gpos[1], gpos[2]};
+      if (type == kGeomCapsule) {
+        const float sg = float(m.con_side[c]);
+        sp[0] += sg * R[2] * sz1; sp[1] += sg * R[5] * sz1; sp[2] += sg * R[8] * sz1;
+      }
+      const float dl[3] = {sp[0] - m.plane_pos[0], sp[1] - m.plane_pos[1], sp[2] - m.plane_pos[2]};
+      dist = dot3(dl, n) - sz0;
+      const float k = sz0 + 0.5f * dist;
+      pos[0] = sp[0] - n[0] * k; pos[1] = sp[1] - n[1] * k; pos[2] = sp[2] - n[2] * k;
+    }
+    // tangent t1: capsule -> projected axis (fallback y/z), otherwise math.make_frame(n)[1]
+    bool have = false;
+    if (type == kGeomCapsule) {
+      const float ax[3] = {R[2], R[5], R[8]};
+      const float na = dot3(n, ax);
+      t1[0] = ax[0] - n[0] * na; t1[1] = ax[1] - n[1] * na; t1[2] = ax[2] - n[2] * na;
+      have = normalize3(t1) >= 0.5f;
+      if (!have) {
+        const bool usey = (-0.5f < n[1]) && (n[1] < 0.5f);
+        t1[0] = 0.f; t1[1] = usey ? 1.f : 0.f; t1[2] = usey ? 0.f : 1.f;
+      }
+    } else {
+      float a[3] = {n[0], n[1], n[2]};
+      normalize3(a);
+      const bool usey = (-0.5f < a[1]) && (a[1] < 0.5f);
+      t1[0] = 0.f; t1[1] = usey ? 1.f : 0.f; t1[2] = usey ? 0.f : 1.f;
+      const float ab = dot3(a, t1);
+      t1[0] -= a[0] * ab; t1[1] -= a[1] * ab; t1[2] -= a[2] * ab;
+      normalize3(t1);
+    }
+    float* off = w.at(m.o_cin + m.c_off) + c * 3;
+    float* st1 = w.at(m.o_cin + m.c_t1) + c * 3;
+    off[0] = pos[0] - com[0]; off[1] = pos[1] - com[1]; off[2] = pos[2] - com[2];
+    st1[0] = t1[0]; st1[1] = t1[1]; st1[2] = t1[2];
+    if (dbg_dist) dbg_dist[c] = dist;
+    cpos = dist - par[9];
+    r.cact = cpos < 0.f;
+    r.mu = par[0];
+    cimp = impedance(par + 4, cpos);
+    ck = par[2]; cb_ = par[3];
+    cD = 1.f / fmaxf(par[1] * (1.f - cimp) / cimp, kMinVal);
+  }
+  float lpos[kLimSlots], lk[kLimSlots], lb[kLimSlots], limp[kLimSlots];
+#pragma unroll
+  for (int q = 0; q < kLimSlots; ++q) {
+    const int l = w.lane + 32 * q;
+    r.lsign[q] = 0.f; lpos[q] = 0.f; lk[q] = lb[q] = limp[q] = 0.f;
+    r.D[4 + q] = 0.f;
+    if (l < m.nlimit) {
+      const float* par = m.lim_par + l * 12;
+      const float qv = qpos[m.lim_qadr[l]];
+      const float dmin = qv - par[0], dmax = par[1] - qv;
+      lpos[q] = fminf(dmin, dmax) - par[2];
+      r.lsign[q] = lpos[q] < 0.f ? (dmin < dmax ? 1.f : -1.f) : 0.f;
+      limp[q] = impedance(par + 6, lpos[q]);
+      lk[q] = par[4]; lb[q] = par[5];
+      r.D[4 + q] = 1.f / fmaxf(par[3] * (1.f - limp[q]) / limp[q], kMinVal);
+    }
+  }
+  __syncwarp();
+  float jq[kRowSlots];
+  apply_J(w, r, w.at(m.o_qvel), jq);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { r.D[k] = cD; r.aref[k] = -cb_ * jq[k] - ck * cimp * cpos; }
+#pragma unroll
+  for (int q = 0; q < kLimSlots; ++q) r.aref[4 + q] = -lb[q] * jq[4 + q] - lk[q] * limp[q] * lpos[q];
+  // rows that do not exist (lane >= ncon, l >= nlimit) must never activate: D = 0, aref = 0 => Jaref = 0 (not < 0)
+  if (w.lane >= m.ncon) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r.D[k] = 0.f; r.aref[k] = 0.f; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- solver.solve (CG)
+struct LSPoint { float alpha, cost, d0, d1; };
+
+template <int N>
+__device__ __forceinline__ void ls_points(const float (&alpha)[N], const float Jaref[kRowSlots], const float jv[kRowSlots],
+                                          const float q0[kRowSlots], const float q1[kRowSlots], const float q2[kRowSlots],
+                                          const float qg[3], LSPoint (&out)[N]) {
+  float a0[N], a1[N], a2[N];
+#pragma unroll
+  for (int p = 0; p < N; ++p) {
+    a0[p] = a1[p] = a2[p] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRowSlots; ++k) {
+      const bool act = (Jaref[k] + alpha[p] * jv[k]) < 0.f;
+      a0[p] += act ? q0[k] : 0.f; a1[p] += act ? q1[k] : 0.f; a2[p] += act ? q2[k] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+      a0[p] += __shfl_xor_sync(FULLMASK, a0[p], o);
+      a1[p] += __shfl_xor_sync(FULLMASK, a1[p], o);
+      a2[p] += __shfl_xor_sync(FULLMASK, a2[p], o);
+    }
+#pragma unroll
+  for (int p = 0; p < N; ++p) {
+    const float t0 = a0[p] + qg[0], t1 = a1[p] + qg[1], t2 = a2[p] + qg[2], a = alpha[p];
+    out[p].alpha = a;
+    out[p].cost = a * a * t2 + a * t1 + t0;
+    out[p].d0 = 2.f * a * t2 + t1;
+    out[p].d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
+  }
+}
+
+struct SolverOut { float qacc[kNvSlots], qfc[kNvSlots], force[kRowSlots]; };
+
+__device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots], const float qas[kNvSlots], SolverOut& so) {
+  const DevModel& m = w.m;
+  float* sx = w.at(m.o_cin + m.c_sx);
+  const float* L1 = w.at(m.o_big);
+  float warm[kNvSlots];
+  vget(w, w.at(m.o_warm), warm);
+
+  // ---- warm-start choice: cost(qacc_warmstart) vs cost(qacc_smooth)
+  float Jw[kRowSlots], Js[kRowSlots], Maw[kNvSlots];
+  apply_J(w, r, w.at(m.o_warm), Jw);
+  mul_m(w, w.at(m.o_warm), Maw);
+  vput(w, sx, qas);
+  __syncwarp();
+  apply_J(w, r, sx, Js);
+  float cw = 0.f, cs = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRowSlots; ++k) {
+    Jw[k] -= r.aref[k]; Js[k] -= r.aref[k];
+    cw += (Jw[k] < 0.f) ? r.D[k] * Jw[k] * Jw[k] : 0.f;
+    cs += (Js[k] < 0.f) ? r.D[k] * Js[k] * Js[k] : 0.f;
+  }
+  float gw = 0.f;
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) gw += (Maw[q] - qfs[q]) * (warm[q] - qas[q]);
+  cw = 0.5f * wsum(cw) + 0.5f * wsum(gw);
+  cs = 0.5f * wsum(cs);  // gauss(qacc_smooth) == 0 exactly
+  const bool use_warm = cw < cs;
+
+  float qacc[kNvSlots], Ma[kNvSlots], Jaref[kRowSlots];
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { qacc[q] = use_warm ? warm[q] : qas[q]; Ma[q] = use_warm ? Maw[q] : qfs[q]; }
+#pragma unroll
+  for (int k = 0; k < kRowSlots; ++k) Jaref[k] = use_warm ? Jw[k] : Js[k];
+
+  float force[kRowSlots], qfc[kNvSlots], grad[kNvSlots], Mgrad[kNvSlots], search[kNvSlots];
+  float gauss, cost = use_warm ? cw : cs, prev_cost = __int_as_float(0x7f800000);
+  auto update_constraint = [&](bool with_cost) {
+    float c = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRowSlots; ++k) {
+      const bool act = Jaref[k] < 0.f;
+      force[k] = act ? r.D[k] * -Jaref[k] : 0.f;
+      c += act ? r.D[k] * Jaref[k] * Jaref[k] : 0.f;
+    }
+    apply_JT(w, r, force, qfc);
+    float g = 0.f;
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) g += (Ma[q] - qfs[q]) * (qacc[q] - qas[q]);
+    gauss = 0.5f * wsum(g);
+    if (with_cost) { prev_cost = cost; cost = 0.5f * wsum(c) + gauss; }
+  };
+  auto update_gradient = [&]() {
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) grad[q] = Ma[q] - qfs[q] - qfc[q];
+    vput(w, sx, grad);
+    __syncwarp();
+    solve_ld(w, L1, sx);
+    vget(w, sx, Mgrad);
+    __syncwarp();
+  };
+  // Context.create: cost = inf -> update_constraint sets prev_cost = inf, cost = c
+  {
+    cost = __int_as_float(0x7f800000);
+    update_constraint(true);
+    update_gradient();
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) search[q] = -Mgrad[q];
+  }
+  const float scale = m.meaninertia_scale;
+  for (int iter = 0;; ++iter) {
+    if (m.iterations != 1) {
+      const float improvement = (prev_cost - cost) / scale;
+      const float gradient = sqrtf(vdot(grad, grad)) / scale;
+      if (iter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
+    } else if (iter >= 1) {
+      break;
+    }
+    // ---- _linesearch
+    const float smag = sqrtf(vdot(search, search)) * scale;
+    const float gtol = m.tolerance * m.ls_tolerance * smag;
+    float mv[kNvSlots], jv[kRowSlots];
+    vput(w, sx, search);
+    __syncwarp();
+    mul_m(w, sx, mv);
+    apply_J(w, r, sx, jv);
+    float qg[3];
+    {
+      float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) { a += search[q] * Ma[q]; b += search[q] * qfs[q]; c += search[q] * mv[q]; }
+      qg[0] = gauss; qg[1] = wsum(a) - wsum(b); qg[2] = 0.5f * wsum(c);
+    }
+    float q0[kRowSlots], q1[kRowSlots], q2[kRowSlots];
+#pragma unroll
+    for (int k = 0; k < kRowSlots; ++k) {
+      q0[k] = 0.5f * Jaref[k] * Jaref[k] * r.D[k];
+      q1[k] = jv[k] * Jaref[k] * r.D[k];
+      q2[k] = 0.5f * jv[k] * jv[k] * r.D[k];
+    }
+    LSPoint p0, lo, hi;
+    {
+      const float a0[1] = {0.f};
+      LSPoint o1[1];
+      ls_points<1>(a0, Jaref, jv, q0, q1, q2, qg, o1);
+      p0 = o1[0];
+      const float a1[1] = {p0.alpha - p0.d0 / p0.d1};
+      ls_points<1>(a1, Jaref, jv, q0, q1, q2, qg, o1);
+      lo = o1[0];
+      const bool lesser = lo.d0 < p0.d0;
+      hi = lesser ? p0 : lo;
+      lo = lesser ? lo : p0;
+    }
+    bool swap = true;
+    for (int it = 0;; ++it) {
+      bool done = it >= m.ls_iterations;
+      done |= !swap;
+      done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+      done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+      if (done) break;
+      const float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+      LSPoint o3[3];
+      ls_points<3>(al, Jaref, jv, q0, q1, q2, qg, o3);
+      const LSPoint lo_next = o3[0], hi_next = o3[1], mid = o3[2];
+      const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+      if (swap_lo_next) lo = lo_next;
+      const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+      if (swap_lo_mid) lo = mid;
+      const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+      if (swap_hi_next) hi = hi_next;
+      const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+      if (swap_hi_mid) hi = mid;
+      swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+    }
+    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+    const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+    if (improved) {
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) { qacc[q] += search[q] * alpha; Ma[q] += mv[q] * alpha; }
+#pragma unroll
+      for (int k = 0; k < kRowSlots; ++k) Jaref[k] += jv[k] * alpha;
+    }
+    // ---- body: update + Polak-Ribiere
+    float pg[kNvSlots], pMg[kNvSlots];
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) { pg[q] = grad[q]; pMg[q] = Mgrad[q]; }
+    update_constraint(true);
+    update_gradient();
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) { num += grad[q] * (Mgrad[q] - pMg[q]); den += pg[q] * pMg[q]; }
+    float beta = wsum(num) / fmaxf(kMinVal, wsum(den));
+    beta = fmaxf(0.f, beta);
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) search[q] = -Mgrad[q] + beta * search[q];
+  }
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { so.qacc[q] = qacc[q]; so.qfc[q] = qfc[q]; }
+#pragma unroll
+  for (int k = 0; k < kRowSlots; ++k) so.force[k] = force[k];
+}
+
+// ---------------------------------------------------------------------------------------------- one mjx.forward
+struct FwdOut {
+  float qfa[kNvSlots], qfs[kNvSlots], qas[kNvSlots], bias[kNvSlots], actdot[2], com[3];
+  SolverOut so;
+};
+
+__device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
+  const DevModel& m = w.m;
+  kinematics(w);
+  com_pos(w, fo.com);
+  com_vel_rne(w, fo.bias);
+  passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
+  __syncwarp();
+  crb_factor(w);
+  float* sx = w.at(m.o_cin + m.c_sx);
+  vput(w, sx, fo.qfs);
+  __syncwarp();
+  solve_ld(w, w.at(m.o_big), sx);
+  vget(w, sx, fo.qas);
+  __syncwarp();
+  Rows r;
+  make_constraint(w, fo.com, r, dbg_dist);
+  solve_cg(w, r, fo.qfs, fo.qas, fo.so);
+  vput(w, w.at(m.o_warm), fo.so.qacc);
+  __syncwarp();
+}
+
+// forward.euler + _advance
+__device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
+  const DevModel& m = w.m;
+  float* sx = w.at(m.o_cin + m.c_sx);
+  float rhs[kNvSlots], qacc[kNvSlots];
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) rhs[q] = fo.qfs[q] + fo.so.qfc[q];
+  vput(w, sx, rhs);
+  __syncwarp();
+  solve_ld(w, w.at(m.o_big + m.nMpad), sx);
+  vget(w, sx, qacc);
+  float* qpos = w.at(m.o_qpos);
+  float* qvel = w.at(m.o_qvel);
+  float* act = w.at(m.o_act);
+  if (m.na) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const int u = w.lane + 32 * k; if (u < m.nu) act[u] = act[u] + fo.actdot[k] * m.dt; }
+  }
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    if (d < m.nv) {
+      const float v = qvel[d] + qacc[q] * m.dt;
+      qvel[d] = v;
+      const int qa = m.dof_qadr[d];
+      if (qa >= 0) qpos[qa] = qpos[qa] + m.dt * v;
+    }
+  }
+  __syncwarp();
+  for (int j = w.lane; j < m.njnt; j += 32) {
+    if (m.jnt_type[j] != kJntFree) continue;
+    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    qpos[qa] = qpos[qa] + m.dt * qvel[da]; qpos[qa + 1] = qpos[qa + 1] + m.dt * qvel[da + 1];
+    qpos[qa + 2] = qpos[qa + 2] + m.dt * qvel[da + 2];
+    float v[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+    const float nrm = normalize3(v);
+    float sn, cs;
+    sincosf(m.dt * nrm * 0.5f, &sn, &cs);
+    const float qr[4] = {cs, v[0] * sn, v[1] * sn, v[2] * sn};
+    float q2[4];
+    qmul(qpos + qa + 3, qr, q2);
+    normalize4(q2);
+    qpos[qa + 3] = q2[0]; qpos[qa + 4] = q2[1]; qpos[qa + 5] = q2[2]; qpos[qa + 6] = q2[3];
+  }
+  time = __fadd_rn(time, m.dt);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- task layer
+__device__ __forceinline__ float nan_to_num(float x) {
+  if (isnan(x)) return 0.f;
+  if (isinf(x)) return x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+  return x;
+}
+// _get_cur_frame (single_clip_tracking.py:452-454): unfused fp32 multiply then add, floor, int
+__device__ __forceinline__ int cur_frame_of(float time, float mocap_hz, int start_frame) {
+  return int(floorf(__fadd_rn(__fmul_rn(time, mocap_hz), float(start_frame))));
+}
+
+// _get_obs (single_clip_tracking.py:394-450) + walker transforms (walker/base.py:170-258); writes obs to global
+__device__ void write_obs(const Warp& w, const DevTask& t, const float* __restrict__ clips, int clip_len, int clip, int frame,
+                          const float qfa[kNvSlots], float* __restrict__ obs, bool& bad) {
+  const DevModel& m = w.m;
+  const TmjxTaskConfig& cfg = t.cfg;
+  const float* qpos = w.at(m.o_qpos);
+  const float* qvel = w.at(m.o_qvel);
+  const float* xpos = w.at(m.o_xpos);
+  const float* xquat = w.at(m.o_xquat);
+  const int L = cfg.traj_length;
+  const int start = min(max(frame + 1, 0), clip_len - L);  // dynamic_slice clamps the start
+  const float quat[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
+  const int nji = cfg.n_joint_idxs, nbi = cfg.n_body_idxs;
+  float* o_track = obs;
+  float* o_quat = o_track + 3 * L;
+  float* o_joint = o_quat + 4 * L;
+  float* o_body = o_joint + nji * L;
+  float* o_prop = o_body + 3 * nbi * L;
+  const size_t base = (size_t(clip) * clip_len + start) * t.frame_stride;
+  for (int i = w.lane; i < L; i += 32) {
+    const float* fr = clips + base + size_t(i) * t.frame_stride;
+    const float dl[3] = {fr[t.o_pos] - qpos[0], fr[t.o_pos + 1] - qpos[1], fr[t.o_pos + 2] - qpos[2]};
+    float r3[3];
+    rot(dl, quat, r3);
+    o_track[i * 3] = nan_to_num(r3[0]); o_track[i * 3 + 1] = nan_to_num(r3[1]); o_track[i * 3 + 2] = nan_to_num(r3[2]);
+    const float rq[4] = {fr[t.o_quat], -fr[t.o_quat + 1], -fr[t.o_quat + 2], -fr[t.o_quat + 3]};
+    float q4[4];
+    qmul(quat, rq, q4);
+    for (int k = 0; k < 4; ++k) o_quat[i * 4 + k] = nan_to_num(q4[k]);
+  }
+  for (int i = w.lane; i < L * nji; i += 32) {
+    const int tt = i / nji, c = t.joint_col[i % nji];
+    const float* fr = clips + base + size_t(tt) * t.frame_stride;
+    o_joint[i] = nan_to_num(fr[t.o_joints + c] - qpos[7 + c]);
+  }
+  for (int i = w.lane; i < L * nbi; i += 32) {
+    const int tt = i / nbi, bi = i % nbi;
+    const float* fr = clips + base + size_t(tt) * t.frame_stride + t.o_bodies + 3 * t.body_slot[bi];
+    const int row = t.body_row[bi] + 1;
+    const float dl[3] = {fr[0] - xpos[row * 3], fr[1] - xpos[row * 3 + 1], fr[2] - xpos[row * 3 + 2]};
+    float r3[3];
+    rot(dl, quat, r3);
+    o_body[i * 3] = nan_to_num(r3[0]); o_body[i * 3 + 1] = nan_to_num(r3[1]); o_body[i * 3 + 2] = nan_to_num(r3[2]);
+  }
+  // proprioception
+  const int nj = m.nq - 7, nvj = m.nv - 6;
+  for (int i = w.lane; i < nj; i += 32) o_prop[i] = nan_to_num(qpos[7 + i]);
+  for (int i = w.lane; i < nvj; i += 32) o_prop[nj + i] = nan_to_num(qvel[6 + i]);
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { const int d = w.lane + 32 * q; if (d < m.nv) o_prop[nj + nvj + d] = nan_to_num(qfa[q]); }
+  float* o_tail = o_prop + nj + nvj + m.nv;
+  const int tb = cfg.torso_body_id;
+  float R[9];
+  q2mat(xquat + tb * 4, R);
+  if (w.lane == 0) {
+    o_tail[0] = nan_to_num(xpos[tb * 3 + 2]);
+    o_tail[1] = nan_to_num(R[6]); o_tail[2] = nan_to_num(R[7]); o_tail[3] = nan_to_num(R[8]);
+  }
+  for (int i = w.lane; i < cfg.n_appendages * 3; i += 32) {
+    const int a = i / 3, c = i % 3, b = cfg.appendage_body_ids[a];
+    const float dl[3] = {xpos[b * 3] - xpos[tb * 3], xpos[b * 3 + 1] - xpos[tb * 3 + 1], xpos[b * 3 + 2] - xpos[tb * 3 + 2]};
+    o_tail[4 + i] = nan_to_num(dl[0] * R[c] + dl[1] * R[3 + c] + dl[2] * R[6 + c]);
+  }
+  (void)bad;
+}
+
+struct KArgs {
+  DevModel m;
+  const DevTask* task;
+  const float* clips;
+  int n_clips, clip_len;
+  TmjxState st;
+  TmjxOut out;
+  const float* action;
+  int n_env;
+  unsigned flags;
+};
+
+template <bool kStep>
+__global__ void __launch_bounds__(128) tmjx_env_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ float smem[];
+  const DevModel& m = a.m;
+  const DevTask& t = *a.task;
+  const TmjxTaskConfig& cfg = t.cfg;
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Warp w{m, smem + size_t(warp) * m.smem_floats, lane};
+  const int nu = m.nu, nobs = t.obs_size, W = cfg.var_window_size;
+  for (int e = blockIdx.x * wpb + warp; e < a.n_env; e += gridDim.x * wpb) {
+    // ---- stage the persistent state
+    float* qpos = w.at(m.o_qpos);
+    float* qvel = w.at(m.o_qvel);
+    float* act = w.at(m.o_act);
+    float* ctrl = w.at(m.o_ctrl);
+    float* warm = w.at(m.o_warm);
+    for (int i = lane; i < m.nq; i += 32) qpos[i] = a.st.qpos[size_t(e) * m.nq + i];
+    for (int i = lane; i < m.nv; i += 32) qvel[i] = a.st.qvel[size_t(e) * m.nv + i];
+    float time;
+    if (kStep) {
+      for (int i = lane; i < m.na; i += 32) act[i] = a.st.act[size_t(e) * m.na + i];
+      for (int i = lane; i < m.nv; i += 32) warm[i] = a.st.qacc_warmstart[size_t(e) * m.nv + i];
+      for (int i = lane; i < nu; i += 32) {
+        float c = a.action[size_t(e) * nu + i];
+        if (m.act_flags[i] & 1) c = fminf(fmaxf(c, m.act_ctrl_lo[i]), m.act_ctrl_hi[i]);
+        ctrl[i] = c;
+      }
+      time = a.st.time[e];
+    } else {
+      for (int i = lane; i < m.na; i += 32) act[i] = 0.f;
+      for (int i = lane; i < m.nv; i += 32) warm[i] = 0.f;
+      for (int i = lane; i < nu; i += 32) ctrl[i] = 0.f;
+      time = 0.f;
+    }
+    float prev_done = 0.f;
+    if (kStep && (a.flags & TMJX_F_AUTORESET)) prev_done = a.out.done[e];
+    __syncwarp();
+
+    FwdOut fo;
+    float* dbg_dist = a.out.dbg_contact_dist ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
+    if (kStep) {
+      for (int f = 0; f < m.n_frames; ++f) {
+        forward(w, fo, f == m.n_frames - 1 ? dbg_dist : nullptr);
+        euler(w, fo, time);
+      }
+    } else {
+      forward(w, fo, dbg_dist);
+    }
+
+    // ---- NaN scan over the state this build materialises (stand-in for ravel_pytree(data), :290-293)
+    bool bad = isnan(time);
+    for (int i = lane; i < m.nq; i += 32) bad |= isnan(qpos[i]);
+    for (int i = lane; i < m.nv; i += 32) bad |= isnan(qvel[i]) || isnan(warm[i]);
+    for (int i = lane; i < m.na; i += 32) bad |= isnan(act[i]);
+    for (int i = lane; i < m.nbody * 3; i += 32) bad |= isnan(w.at(m.o_xpos)[i]);
+    for (int i = lane; i < m.nbody * 4; i += 32) bad |= isnan(w.at(m.o_xquat)[i]);
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) bad |= isnan(fo.qfa[q]) || isnan(fo.so.qfc[q]) || isnan(fo.bias[q]) || isnan(fo.qas[q]);
+#pragma unroll
+    for (int k = 0; k < kRowSlots; ++k) bad |= isnan(fo.so.force[k]);
+    bad = __any_sync(FULLMASK, bad);
+
+    const int clip = a.st.clip_idx[e], sf = a.st.start_frame[e];
+    const int frame = cur_frame_of(time, cfg.mocap_hz, sf);
+    float* obs = a.out.obs + size_t(e) * nobs;
+    float done = 0.f;
+
+    if (kStep) {
+      const float* xpos = w.at(m.o_xpos);
+      const int fcl = min(max(frame, 0), a.clip_len - 1);
+      const float* fr = a.clips + (size_t(clip) * a.clip_len + fcl) * t.frame_stride;
+      const float* action = a.action + size_t(e) * nu;
+      // info updates (:227-234)
+      float* buf = a.st.action_buffer + size_t(e) * W * nu;
+      int idx = a.st.buffer_index[e];
+      float a2 = 0.f;
+      for (int i = lane; i < nu; i += 32) {
+        const float v = action[i];
+        a.st.prev_ctrl[size_t(e) * nu + i] = v;
+        buf[idx * nu + i] = v;
+        a2 += v * v;
+      }
+      const int idx_w = idx;
+      idx = (idx + 1) % W;
+      // ---- compute_tracking_rewards (reward.py:359-485)
+      const float pd[3] = {qpos[0] - fr[t.o_pos], qpos[1] - fr[t.o_pos + 1], qpos[2] - fr[t.o_pos + 2]};
+      const float pos_reward = cfg.pos_reward_weight * expf(-cfg.pos_reward_exp_scale * (pd[0] * pd[0] + pd[1] * pd[1] + pd[2] * pd[2]));
+      float qs[4] = {qpos[3], qpos[4], qpos[5], qpos[6]}, qt[4] = {fr[t.o_quat], fr[t.o_quat + 1], fr[t.o_quat + 2], fr[t.o_quat + 3]};
+      {
+        const float ns = sqrtf(qs[0] * qs[0] + qs[1] * qs[1] + qs[2] * qs[2] + qs[3] * qs[3]);
+        const float nt = sqrtf(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+        for (int k = 0; k < 4; ++k) { qs[k] = qs[k] / ns; qt[k] = qt[k] / nt; }
+      }
+      const float qd = qs[0] * qt[0] + qs[1] * qt[1] + qs[2] * qt[2] + qs[3] * qt[3];
+      const float bq = 0.5f * acosf(fminf(1.f, 2.f * qd * qd - 1.f));
+      const float quat_distance = bq * bq;
+      const float quat_reward = cfg.quat_reward_weight * expf(-cfg.quat_reward_exp_scale * quat_distance);
+      float jd = 0.f;
+      for (int j = lane; j < m.nq - 7; j += 32) { const float x = qpos[7 + j] - fr[t.o_joints + j]; jd += x * x; }
+      const float joint_distance = wsum(jd);
+      const float joint_reward = cfg.joint_reward_weight * expf(-cfg.joint_reward_exp_scale * joint_distance);
+      float av = 0.f;
+      for (int k = 0; k < 3; ++k) { const float x = qvel[3 + k] - fr[t.o_angvel + k]; av += x * x; }
+      const float angvel_reward = cfg.angvel_reward_weight * expf(-cfg.angvel_reward_exp_scale * av);
+      float be = 0.f, ee = 0.f;
+      for (int i = lane; i < cfg.n_body_idxs * 3; i += 32) {
+        const int bi = i / 3, k = i % 3;
+        const float x = xpos[(t.body_row[bi] + 1) * 3 + k] - fr[t.o_bodies + 3 * t.body_slot[bi] + k];
+        be += x * x;
+      }
+      for (int i = lane; i < cfg.n_endeff_idxs * 3; i += 32) {
+        const int bi = i / 3, k = i % 3;
+        const float x = xpos[(t.endeff_row[bi] + 1) * 3 + k] - fr[t.o_bodies + 3 * t.endeff_slot[bi] + k];
+        ee += x * x;
+      }
+      const float bodypos_reward = cfg.bodypos_reward_weight * expf(-cfg.bodypos_reward_exp_scale * wsum(be));
+      const float endeff_reward = cfg.endeff_reward_weight * expf(-cfg.endeff_reward_exp_scale * wsum(ee));
+      const float ctrl_cost = cfg.ctrl_cost_weight * wsum(a2);
+      const float ctrl_diff_cost = cfg.ctrl_diff_cost_weight * 0.f;  // prev_ctrl was overwritten first (:227)
+      float en = 0.f;
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d >= 6 && d < m.nv) en += fabsf(qvel[d]) * fabsf(fo.qfa[q]); }
+      const float energy_cost = cfg.energy_cost_weight * fminf(wsum(en), 50.f);
+      const float torso_z = xpos[cfg.torso_idx * 3 + 2];
+      float healthy = torso_z < cfg.healthy_z_min ? 0.f : 1.f;
+      if (torso_z > cfg.healthy_z_max) healthy = 0.f;
+      const float fall = 1.f - healthy;
+      float summed = 0.f;
+      for (int k = 0; k < 3; ++k) { const float x = pd[k] * cfg.penalty_pos_distance_scale[k]; summed += x * x; }
+      const float too_far = summed > cfg.too_far_dist ? 1.f : 0.f;
+      const float bad_pose = joint_distance > cfg.bad_pose_dist ? 1.f : 0.f;
+      const float bad_quat = quat_distance > cfg.bad_quat_dist ? 1.f : 0.f;
+      // windowed variance + jerk over the ring buffer (reward.py:314-356); lane k owns columns k, k+32
+      float var_sum = 0.f, jerk = 0.f;
+      for (int k = lane; k < nu; k += 32) {
+        const float mine = action[k];
+        float mean = 0.f;
+        for (int tt = 0; tt < W; ++tt) mean += (tt == idx_w) ? mine : buf[tt * nu + k];
+        mean = mean / float(W);
+        float v = 0.f;
+        for (int tt = 0; tt < W; ++tt) { const float x = ((tt == idx_w) ? mine : buf[tt * nu + k]) - mean; v += x * x; }
+        var_sum += v / float(W);
+        float b0 = 0.f, b1 = 0.f;
+        for (int tt = 0; tt < W; ++tt) {
+          const int rr = (idx + tt) % W;
+          const float b2 = (rr == idx_w) ? mine : buf[rr * nu + k];
+          if (tt >= 2) { const float x = b2 - 2.f * b1 + b0; jerk += x * x; }
+          b0 = b1; b1 = b2;
+        }
+      }
+      const float var_cost = cfg.var_coeff * wsum(var_sum);
+      const float jerk_cost = cfg.jerk_coeff * wsum(jerk);
+
+      write_obs(w, t, a.clips, a.clip_len, clip, frame, fo.qfa, obs, bad);
+      float reward = joint_reward + pos_reward + quat_reward + angvel_reward + bodypos_reward + endeff_reward - ctrl_cost -
+                     ctrl_diff_cost - energy_cost - var_cost - jerk_cost;
+      done = fmaxf(fmaxf(fall, too_far), fmaxf(bad_pose, bad_quat));
+      reward = nan_to_num(reward);
+      const float nanv = bad ? 1.f : 0.f;
+      done = fmaxf(nanv, done);
+      if (lane == 0) {
+        float* mt = a.out.metrics + size_t(e) * TMJX_N_METRICS;
+        mt[TMJX_M_POS_REWARD] = pos_reward; mt[TMJX_M_QUAT_REWARD] = quat_reward; mt[TMJX_M_JOINT_REWARD] = joint_reward;
+        mt[TMJX_M_ANGVEL_REWARD] = angvel_reward; mt[TMJX_M_BODYPOS_REWARD] = bodypos_reward; mt[TMJX_M_ENDEFF_REWARD] = endeff_reward;
+        mt[TMJX_M_CTRL_COST] = -ctrl_cost; mt[TMJX_M_CTRL_DIFF_COST] = -ctrl_diff_cost; mt[TMJX_M_ENERGY_COST] = -energy_cost;
+        mt[TMJX_M_DONE] = done; mt[TMJX_M_TOO_FAR] = too_far; mt[TMJX_M_BAD_POSE] = bad_pose; mt[TMJX_M_BAD_QUAT] = bad_quat;
+        mt[TMJX_M_FALL] = fall; mt[TMJX_M_NAN] = nanv; mt[TMJX_M_JOINT_DISTANCE] = joint_distance;
+        mt[TMJX_M_SUMMED_POS_DISTANCE] = summed; mt[TMJX_M_QUAT_DISTANCE] = quat_distance; mt[TMJX_M_VAR_COST] = -var_cost;
+        mt[TMJX_M_JERK_COST] = -jerk_cost;
+        a.out.reward[e] = reward;
+        a.out.cur_frame[e] = frame;
+        a.st.buffer_index[e] = idx;
+      }
+    } else {
+      write_obs(w, t, a.clips, a.clip_len, clip, frame, fo.qfa, obs, bad);
+      for (int i = lane; i < TMJX_N_METRICS; i += 32) a.out.metrics[size_t(e) * TMJX_N_METRICS + i] = 0.f;
+      for (int i = lane; i < W * nu; i += 32) a.st.action_buffer[size_t(e) * W * nu + i] = 0.f;
+      for (int i = lane; i < nu; i += 32) a.st.prev_ctrl[size_t(e) * nu + i] = 0.f;
+      if (lane == 0) { a.out.reward[e] = 0.f; a.out.cur_frame[e] = frame; a.st.buffer_index[e] = 0; }
+    }
+
+    // ---- debug taps
+    if (a.out.dbg_qacc) for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.out.dbg_qacc[size_t(e) * m.nv + d] = fo.so.qacc[q]; }
+    if (a.out.dbg_qacc_smooth) for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.out.dbg_qacc_smooth[size_t(e) * m.nv + d] = fo.qas[q]; }
+    if (a.out.dbg_qfrc_bias) for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.out.dbg_qfrc_bias[size_t(e) * m.nv + d] = fo.bias[q]; }
+    if (a.out.dbg_qfrc_constraint) for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.out.dbg_qfrc_constraint[size_t(e) * m.nv + d] = fo.so.qfc[q]; }
+    if (a.out.dbg_efc_force) {  // MJX row order: limits, then 4 rows per contact
+      float* ef = a.out.dbg_efc_force + size_t(e) * m.nefc;
+      for (int q = 0; q < kLimSlots; ++q) { const int l = lane + 32 * q; if (l < m.nlimit) ef[l] = fo.so.force[4 + q]; }
+      if (lane < m.ncon) for (int k = 0; k < 4; ++k) ef[m.nlimit + lane * 4 + k] = fo.so.force[k];
+    }
+    if (a.out.dbg_subtree_com && lane < 3) a.out.dbg_subtree_com[size_t(e) * 3 + lane] = fo.com[lane];
+
+    // ---- wrappers (brax EpisodeWrapper + auto-reset, wrappers.py:104-144) when fused
+    bool restore = false;
+    if (kStep && (a.flags & TMJX_F_AUTORESET)) {
+      float steps = a.st.steps[e];
+      if (prev_done != 0.f) steps = 0.f;
+      steps = steps + 1.f;
+      const bool over = steps >= float(cfg.episode_length);
+      const float trunc = over ? 1.f - done : 0.f;
+      if (over) done = 1.f;
+      if (lane == 0) { a.st.steps[e] = steps; a.st.truncation[e] = trunc; }
+      restore = done != 0.f;
+    }
+    if (lane == 0) a.out.done[e] = done;
+
+    // ---- write back the pipeline state (or the stored first state where done)
+    __syncwarp();
+    if (!restore) {
+      for (int i = lane; i < m.nq; i += 32) a.st.qpos[size_t(e) * m.nq + i] = qpos[i];
+      for (int i = lane; i < m.nv; i += 32) { a.st.qvel[size_t(e) * m.nv + i] = qvel[i]; a.st.qacc_warmstart[size_t(e) * m.nv + i] = warm[i]; }
+      for (int i = lane; i < m.na; i += 32) a.st.act[size_t(e) * m.na + i] = act[i];
+      for (int i = lane; i < m.nbody * 3; i += 32) a.st.xpos[size_t(e) * m.nbody * 3 + i] = w.at(m.o_xpos)[i];
+      for (int i = lane; i < m.nbody * 4; i += 32) a.st.xquat[size_t(e) * m.nbody * 4 + i] = w.at(m.o_xquat)[i];
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.st.qfrc_actuator[size_t(e) * m.nv + d] = fo.qfa[q]; }
+      if (lane == 0) a.st.time[e] = time;
+    } else {
+      for (int i = lane; i < m.nq; i += 32) a.st.qpos[size_t(e) * m.nq + i] = a.st.first_qpos[size_t(e) * m.nq + i];
+      for (int i = lane; i < m.nv; i += 32) {
+        a.st.qvel[size_t(e) * m.nv + i] = a.st.first_qvel[size_t(e) * m.nv + i];
+        a.st.qacc_warmstart[size_t(e) * m.nv + i] = a.st.first_qacc_warmstart[size_t(e) * m.nv + i];
+        a.st.qfrc_actuator[size_t(e) * m.nv + i] = a.st.first_qfrc_actuator[size_t(e) * m.nv + i];
+      }
+      for (int i = lane; i < m.na; i += 32) a.st.act[size_t(e) * m.na + i] = a.st.first_act[size_t(e) * m.na + i];
+      for (int i = lane; i < m.nbody * 3; i += 32) a.st.xpos[size_t(e) * m.nbody * 3 + i] = a.st.first_xpos[size_t(e) * m.nbody * 3 + i];
+      for (int i = lane; i < m.nbody * 4; i += 32) a.st.xquat[size_t(e) * m.nbody * 4 + i] = a.st.first_xquat[size_t(e) * m.nbody * 4 + i];
+      for (int i = lane; i < nobs; i += 32) obs[i] = a.st.first_obs[size_t(e) * nobs + i];
+      for (int i = lane; i < nu; i += 32) a.st.prev_ctrl[size_t(e) * nu + i] = a.st.first_prev_ctrl[size_t(e) * nu + i];
+      if (lane == 0) a.st.time[e] = a.st.first_time[e];
+    }
+    if (!kStep && (a.flags & TMJX_F_SNAPSHOT)) {
+      for (int i = lane; i < m.nq; i += 32) a.st.first_qpos[size_t(e) * m.nq + i] = qpos[i];
+      for (int i = lane; i < m.nv; i += 32) { a.st.first_qvel[size_t(e) * m.nv + i] = qvel[i]; a.st.first_qacc_warmstart[size_t(e) * m.nv + i] = warm[i]; }
+      for (int i = lane; i < m.na; i += 32) a.st.first_act[size_t(e) * m.na + i] = act[i];
+      for (int i = lane; i < m.nbody * 3; i += 32) a.st.first_xpos[size_t(e) * m.nbody * 3 + i] = w.at(m.o_xpos)[i];
+      for (int i = lane; i < m.nbody * 4; i += 32) a.st.first_xquat[size_t(e) * m.nbody * 4 + i] = w.at(m.o_xquat)[i];
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d < m.nv) a.st.first_qfrc_actuator[size_t(e) * m.nv + d] = fo.qfa[q]; }
+      __syncwarp();
+      for (int i = lane; i < nobs; i += 32) a.st.first_obs[size_t(e) * nobs + i] = obs[i];
+      for (int i = lane; i < nu; i += 32) a.st.first_prev_ctrl[size_t(e) * nu + i] = 0.f;
+      if (lane == 0) { a.st.first_time[e] = time; a.st.steps[e] = 0.f; a.st.truncation[e] = 0.f; }
+    }
+    __syncwarp();
+  }
+}
+
+// FP32 FMA-throughput microbenchmark (roofline denominator)
+__global__ void fma_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 1.000001f, c = 1e-7f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tmjx
+
+// =============================================================================================== C ABI
+using namespace tmjx;
+
+struct TmjxModel {
+  DevModel dm;
+  DevTask task;
+  DevTask* d_task = nullptr;
+  int* d_i32 = nullptr;
+  uint16_t* d_u16 = nullptr;
+  uint8_t* d_u8 = nullptr;
+  float* d_f32 = nullptr;
+  int device = 0, sm_count = 0, envs_per_block = 4, max_blocks_per_sm = 1;
+  size_t smem_per_block = 0;
+  TmjxTaskConfig cfg;
+};
+struct TmjxClips {
+  float* d_table = nullptr;
+  size_t bytes = 0;
+  int n_clips = 0, clip_len = 0;
+  int device = 0;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(TMJX_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+int tmjx_abi_version(void) { return TMJX_ABI_VERSION; }
+const char* tmjx_last_error(void) { return g_err.c_str(); }
+
+int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg, int device, TmjxModel** out) {
+  if (!blob || !cfg || !out) return fail(TMJX_E_ARG, "null argument");
+  if (cfg->abi_version != TMJX_ABI_VERSION) return fail(TMJX_E_ARG, "TmjxTaskConfig.abi_version mismatch");
+  HostTables t;
+  try {
+    Blob b(blob, nbytes);
+    build_tables(b, *cfg, t);
+  } catch (const std::exception& e) {
+    const std::string msg = e.what();
+    return fail(msg.find("unsupported") != std::string::npos || msg.find("only") != std::string::npos ? TMJX_E_UNSUPPORTED : TMJX_E_BLOB, msg);
+  }
+  CU(cudaSetDevice(device));
+  auto* m = new TmjxModel();
+  m->device = device;
+  m->cfg = *cfg;
+  CU(cudaMalloc(&m->d_i32, std::max<size_t>(t.i32.size(), 1) * 4));
+  CU(cudaMalloc(&m->d_u16, std::max<size_t>(t.u16.size(), 1) * 2));
+  CU(cudaMalloc(&m->d_u8, std::max<size_t>(t.u8.size(), 1)));
+  CU(cudaMalloc(&m->d_f32, std::max<size_t>(t.f32.size(), 1) * 4));
+  CU(cudaMemcpy(m->d_i32, t.i32.data(), t.i32.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(m->d_u16, t.u16.data(), t.u16.size() * 2, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(m->d_u8, t.u8.data(), t.u8.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(m->d_f32, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice));
+  m->dm = t.dm;
+  relocate(m->dm, m->d_i32, m->d_u16, m->d_u8, m->d_f32);
+  build_task(m->dm, *cfg, /*n_ref_bodies=*/m->dm.nbody - 1, m->task);
+  CU(cudaMalloc(&m->d_task, sizeof(DevTask)));
+  CU(cudaMemcpy(m->d_task, &m->task, sizeof(DevTask), cudaMemcpyHostToDevice));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  m->sm_count = prop.multiProcessorCount;
+  const size_t per_env = size_t(m->dm.smem_floats) * 4;
+  m->envs_per_block = 4;
+  m->smem_per_block = per_env * m->envs_per_block;
+  if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
+  m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  *out = m;
+  return TMJX_OK;
+}
+
+void tmjx_model_destroy(TmjxModel* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_i32); cudaFree(m->d_u16); cudaFree(m->d_u8); cudaFree(m->d_f32); cudaFree(m->d_task);
+  delete m;
+}
+
+int tmjx_model_dims(const TmjxModel* m, TmjxDims* d) {
+  if (!m || !d) return fail(TMJX_E_ARG, "null argument");
+  d->nq = m->dm.nq; d->nv = m->dm.nv; d->nu = m->dm.nu; d->na = m->dm.na; d->nbody = m->dm.nbody; d->njnt = m->dm.njnt;
+  d->ncon = m->dm.ncon; d->nefc = m->dm.nefc;
+  d->obs_size = m->task.obs_size; d->reference_obs_size = m->task.ref_obs_size; d->proprioceptive_obs_size = m->task.prop_obs_size;
+  d->var_window_size = m->cfg.var_window_size; d->n_metrics = TMJX_N_METRICS;
+  d->smem_bytes_per_env = m->dm.smem_floats * 4; d->envs_per_block = m->envs_per_block; d->threads_per_env = 32;
+  return TMJX_OK;
+}
+
+int tmjx_clips_create(const TmjxModel* m, const float* position, const float* quaternion, const float* joints,
+                      const float* body_positions, const float* velocity, const float* angular_velocity,
+                      const float* joints_velocity, const float* body_quaternions, int n_clips, int clip_len,
+                      int n_ref_bodies, TmjxClips** out) {
+  (void)velocity; (void)joints_velocity; (void)body_quaternions;  // not read by reward / obs
+  if (!m || !position || !quaternion || !joints || !body_positions || !angular_velocity || !out) return fail(TMJX_E_ARG, "null argument");
+  if (n_clips <= 0 || clip_len < m->cfg.traj_length) return fail(TMJX_E_ARG, "bad clip table shape");
+  if (n_ref_bodies != m->dm.nbody - 1) return fail(TMJX_E_ARG, "body_positions must have nbody-1 rows (stac-mjx layout without `floor`)");
+  const DevTask& t = m->task;
+  const int nj = m->dm.nq - 7;
+  const std::vector<int> rows = task_rows(t);
+  const size_t nf = size_t(n_clips) * clip_len;
+  std::vector<float> tab(nf * t.frame_stride, 0.f);
+  for (size_t f = 0; f < nf; ++f) {
+    float* o = tab.data() + f * t.frame_stride;
+    for (int k = 0; k < 3; ++k) o[t.o_pos + k] = position[f * 3 + k];
+    for (int k = 0; k < 4; ++k) o[t.o_quat + k] = quaternion[f * 4 + k];
+    for (int k = 0; k < 3; ++k) o[t.o_angvel + k] = angular_velocity[f * 3 + k];
+    for (int k = 0; k < nj; ++k) o[t.o_joints + k] = joints[f * nj + k];
+    for (int r = 0; r < t.n_rows; ++r)
+      for (int k = 0; k < 3; ++k) o[t.o_bodies + 3 * r + k] = body_positions[(f * n_ref_bodies + rows[r]) * 3 + k];
+  }
+  CU(cudaSetDevice(m->device));
+  auto* c = new TmjxClips();
+  c->device = m->device; c->n_clips = n_clips; c->clip_len = clip_len; c->bytes = tab.size() * 4;
+  CU(cudaMalloc(&c->d_table, c->bytes));
+  CU(cudaMemcpy(c->d_table, tab.data(), c->bytes, cudaMemcpyHostToDevice));
+  *out = c;
+  return TMJX_OK;
+}
+void tmjx_clips_destroy(TmjxClips* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_table);
+  delete c;
+}
+size_t tmjx_clips_device_bytes(const TmjxClips* c) { return c ? c->bytes : 0; }
+
+}  // extern "C"
+
+static int check_common(const TmjxModel* m, const TmjxClips* c, const TmjxState* s, const TmjxOut* o, int n_env) {
+  if (!m || !c || !s || !o) return fail(TMJX_E_ARG, "null argument");
+  if (n_env <= 0) return fail(TMJX_E_ARG, "n_env must be positive");
+  if (!s->qpos || !s->qvel || !s->act || !s->time || !s->qacc_warmstart || !s->xpos || !s->xquat || !s->qfrc_actuator ||
+      !s->clip_idx || !s->start_frame || !s->buffer_index || !s->prev_ctrl || !s->action_buffer)
+    return fail(TMJX_E_ARG, "TmjxState has a null required buffer");
+  if (!o->obs || !o->reward || !o->done || !o->metrics || !o->cur_frame) return fail(TMJX_E_ARG, "TmjxOut has a null required buffer");
+  if (o->dbg_qM) return fail(TMJX_E_UNSUPPORTED, "dbg_qM is not produced by the CUDA path (the inertia is never dense) (unsupported)");
+  return TMJX_OK;
+}
+static bool has_first(const TmjxState* s) {
+  return s->steps && s->truncation && s->first_qpos && s->first_qvel && s->first_act && s->first_time && s->first_qacc_warmstart &&
+         s->first_xpos && s->first_xquat && s->first_qfrc_actuator && s->first_obs && s->first_prev_ctrl;
+}
+template <bool kStep>
+static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, TmjxState* s, TmjxOut* o, int n_env, unsigned flags,
+                  void* stream) {
+  KArgs a;
+  a.m = m->dm; a.task = m->d_task; a.clips = c->d_table; a.n_clips = c->n_clips; a.clip_len = c->clip_len;
+  a.st = *s; a.out = *o; a.action = action; a.n_env = n_env; a.flags = flags;
+  const int epb = m->envs_per_block;
+  const int need = (n_env + epb - 1) / epb;
+  const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
+  tmjx_env_kernel<kStep><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  CU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+extern "C" {
+
+int tmjx_forward(const TmjxModel* m, const TmjxClips* c, TmjxState* s, TmjxOut* o, int n_env, unsigned flags, void* stream) {
+  int rc = check_common(m, c, s, o, n_env);
+  if (rc) return rc;
+  if ((flags & TMJX_F_SNAPSHOT) && !has_first(s)) return fail(TMJX_E_ARG, "TMJX_F_SNAPSHOT needs the first_* / steps / truncation buffers");
+  return launch<false>(m, c, nullptr, s, o, n_env, flags, stream);
+}
+
+int tmjx_step(const TmjxModel* m, const TmjxClips* c, const float* action, TmjxState* s, TmjxOut* o, int n_env, unsigned flags,
+              void* stream) {
+  int rc = check_common(m, c, s, o, n_env);
+  if (rc) return rc;
+  if (!action) return fail(TMJX_E_ARG, "null action");
+  if ((flags & TMJX_F_AUTORESET) && !has_first(s)) return fail(TMJX_E_ARG, "TMJX_F_AUTORESET needs the first_* / steps / truncation buffers");
+  return launch<true>(m, c, action, s, o, n_env, flags, stream);
+}
+
+double tmjx_fp32_peak_tflops(int device, void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  float* d = nullptr;
+  if (cudaMalloc(&d, size_t(blocks) * threads * 4) != cudaSuccess) return -1.0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  fma_peak_kernel<<<blocks, threads, 0, st>>>(d, 1024);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    fma_peak_kernel<<<blocks, threads, 0, st>>>(d, iters);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * double(iters) * blocks * threads;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+/*
+ * tmjx_tables.h — device-side model tables for the rodent-tracking step kernel, and the host code that
+ * derives them from the model-constant blob (include/tmjx_blob.h).
+ *
+ * Everything the kernel needs from `mjx.Model` (reference single_clip_tracking.py:74,91) is re-laid-out here
+ * for a warp-per-environment execution: bodies sorted by tree depth (level-parallel kinematics), child lists
+ * (deterministic leaf-to-root gathers), MuJoCo-style sparse rows for the joint-space inertia (row i = dof i and
+ * its ancestors), the column view of the same sparsity (descendant lists) for scatter-form triangular solves,
+ * and a Jacobian-free description of the plane contacts (contact bodies + their dof chains).
+ */
+#ifndef TMJX_TABLES_H_
+#define TMJX_TABLES_H_
+
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tmjx.h"
+#include "../../include/tmjx_blob.h"
+
+namespace tmjx {
+
+constexpr int kNvSlots = 3;     // nv <= 96: lane l owns dofs l, l+32, l+64
+constexpr int kLimSlots = 3;    // nlimit <= 96
+constexpr int kMaxCon = 32;     // one lane per contact
+constexpr int kRowSlots = 4 + kLimSlots;  // constraint rows owned by a lane: 4 pyramid rows of contact `lane` + 3 limits
+
+enum { kGeomSphere = 2, kGeomCapsule = 3, kGeomEllipsoid = 4 };
+enum { kJntFree = 0, kJntHinge = 3 };
+
+/* Plain-old-data view passed to the kernel by value (lives in the constant bank). All pointers are device
+ * pointers into one int32, one uint16, one uint8 and one float allocation. */
+struct DevModel {
+  int nq, nv, nu, na, nbody, njnt, nlevel, nM, ncg, ncon, ncb, nlimit, nefc, maxdepth;
+  int n_frames, solver, iterations, ls_iterations;
+  float dt, gravity[3], tolerance, ls_tolerance, meaninertia_scale /* meaninertia * max(1, nv) */, impratio;
+  float plane_pos[3], plane_n[3];
+  float tree_mass;  // total mass of the moving tree (fp32 sum in body order)
+  int tree_root;    // body id of the root of the moving tree
+  // ---- per body
+  const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *lvl_start, *lvl_body, *child_start,
+      *child;
+  const float *body_pos, *body_quat, *body_ipos, *body_iquat, *body_inertia, *body_mass, *body_tree_mass;
+  // ---- per joint
+  const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_body;
+  const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_qpos0, *jnt_springref;
+  // ---- per dof
+  const int *dof_body, *dof_jnt, *dof_madr, *dof_depth, *dof_limit /* limit row or -1 */, *dof_qadr /* hinge: qpos adr, else -1 */;
+  const float *dof_armature, *dof_damping;
+  // ---- sparse inertia structure
+  const uint8_t *m_anc /* [nM] dof id at (row, position) */, *m_row, *m_col /* entry -> (i, j) */, *tri_a, *tri_b;
+  const int* desc_start;      /* [nv+1] */
+  const uint8_t* desc_dof;    /* descendant dof id */
+  const uint16_t* desc_off;   /* offset of L[desc][j] in the sparse array */
+  // ---- actuators
+  const float *act_gain, *act_ctrl_lo, *act_ctrl_hi, *act_dyn_inv /* max(dynprm[0], mjMINVAL): the filter time constant (divisor) */, *act_bias /* [nu,3] */,
+      *act_force_lo, *act_force_hi;
+  const int* act_flags;       /* bit0 ctrllimited, bit1 filter, bit2 affine bias, bit3 forcelimited */
+  const int *dof_act_start, *dof_act_id;
+  const float* dof_act_coef;  /* moment entries, CSR by dof */
+  const int *act_mom_start, *act_mom_dof;
+  const float* act_mom_coef;  /* same entries, CSR by actuator (affine bias length / velocity) */
+  // ---- joint limits (row l)
+  const int *lim_dof, *lim_qadr;
+  const float* lim_par;       /* [nlimit, 12]: lo hi margin invweight k b dmin dmax width mid power pad */
+  // ---- contacts
+  const int *cg_type, *cg_body, *cg_cb;
+  const float *cg_pos, *cg_quat, *cg_size;
+  const int *con_geom, *con_side /* +1 / -1 capsule end, 0 single */, *con_cb;
+  const float* con_par;       /* [ncon, 12]: mu invweight k b dmin dmax width mid power includemargin pad pad */
+  const int *cb_body, *cb_chain_start, *cb_chain_dof, *dof_cb_start, *dof_cb, *cb_con_start, *cb_con;
+  // ---- shared-memory layout (float offsets inside one environment's slice)
+  int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_cdof, o_cin, o_big, smem_floats;
+  // phase A members of o_big
+  int a_xipos, a_anchor, a_axis, a_cvel, a_cdofdot, a_cacc, a_force;
+  // phase B members: L1 at o_big, L2 at o_big + nMpad; f (M build) aliases L2
+  int nMpad;
+  // solver-phase scratch inside o_cin
+  int c_sx, c_sy, c_sD, c_sV, c_sW, c_sWb, c_off, c_t1, c_lf, c_end;
+};
+
+/* Task-layer constants + packed clip table. */
+struct DevTask {
+  TmjxTaskConfig cfg;
+  int obs_size, ref_obs_size, prop_obs_size, n_rows /* packed body rows per frame */, frame_stride;
+  int o_pos, o_quat, o_angvel, o_joints, o_bodies;  // offsets inside a packed frame
+  int body_slot[TMJX_MAX_IDX], endeff_slot[TMJX_MAX_IDX];  // index table entry -> packed row
+  int body_row[TMJX_MAX_IDX], endeff_row[TMJX_MAX_IDX];    // index table entry -> clamped 67-row index
+  int joint_col[TMJX_MAX_IDX];                              // joint_idxs - 1, wrapped + clamped
+};
+
+struct HostTables {
+  std::vector<int32_t> i32;
+  std::vector<uint16_t> u16;
+  std::vector<uint8_t> u8;
+  std::vector<float> f32;
+  DevModel dm{};  // pointers hold OFFSETS until relocate()
+  std::vector<int> packed_rows;  // unused here; task layer
+};
+
+namespace detail {
+template <class T> size_t push(std::vector<T>& pool, const std::vector<T>& v, size_t align = 4) {
+  while (pool.size() % align) pool.push_back(T());
+  size_t off = pool.size();
+  pool.insert(pool.end(), v.begin(), v.end());
+  return off;
+}
+inline int pad4(int n) { return (n + 3) & ~3; }
+}  // namespace detail
+
+#define TMJX_OFF(T, off) reinterpret_cast<const T*>(static_cast<uintptr_t>(off))
+
+/* Build all tables. Pointer members of `dm` temporarily hold element offsets into the four pools; the caller
+ * uploads the pools and calls relocate(). Throws std::runtime_error for models outside the supported subset. */
+inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t) {
+  using detail::pad4;
+  using detail::push;
+  DevModel& m = t.dm;
+  auto dims = b.i32("dims");
+  m.nq = dims[0]; m.nv = dims[1]; m.nu = dims[2]; m.na = dims[3]; m.nbody = dims[4]; m.njnt = dims[5]; m.ncg = dims[6];
+  m.ncon = dims[7]; m.nefc = dims[8];
+  auto opt = b.f32("opt");
+  m.dt = cfg.mj_model_timestep;
+  m.gravity[0] = opt[1]; m.gravity[1] = opt[2]; m.gravity[2] = opt[3];
+  m.tolerance = opt[4]; m.ls_tolerance = opt[5]; m.impratio = opt[6];
+  m.meaninertia_scale = opt[7] * float(std::max(1, m.nv));
+  m.n_frames = cfg.physics_steps_per_control_step; m.solver = cfg.solver; m.iterations = cfg.iterations;
+  m.ls_iterations = cfg.ls_iterations;
+  if (m.solver != TMJX_SOLVER_CG) throw std::runtime_error("only the CG solver is built in this round");
+  if (m.nv > 32 * kNvSlots) throw std::runtime_error("nv > 96 unsupported");
+  if (m.ncon > kMaxCon) throw std::runtime_error("ncon > 32 unsupported");
+  if (m.na != 0 && m.na != m.nu) throw std::runtime_error("na must be 0 or nu");
+
+  const int nbody = m.nbody, njnt = m.njnt, nv = m.nv, nu = m.nu;
+  auto body_parent = b.i32("body_parentid"), body_rootid = b.i32("body_rootid"), body_jntadr = b.i32("body_jntadr"),
+       body_jntnum = b.i32("body_jntnum"), body_dofadr = b.i32("body_dofadr"), body_dofnum = b.i32("body_dofnum"),
+       jnt_type = b.i32("jnt_type"), jnt_qposadr = b.i32("jnt_qposadr"), jnt_dofadr = b.i32("jnt_dofadr"),
+       jnt_bodyid = b.i32("jnt_bodyid"), dof_bodyid = b.i32("dof_bodyid"), dof_jntid = b.i32("dof_jntid"),
+       dof_parentid = b.i32("dof_parentid"), jnt_limited = b.i32("jnt_limited");
+  for (int j = 0; j < njnt; ++j)
+    if (jnt_type[j] != kJntFree && jnt_type[j] != kJntHinge) throw std::runtime_error("only free/hinge joints");
+
+  // ---- tree levels and child lists
+  std::vector<int> depth(nbody, 0);
+  int nlevel = 1;
+  for (int i = 1; i < nbody; ++i) { depth[i] = depth[body_parent[i]] + 1; nlevel = std::max(nlevel, depth[i] + 1); }
+  std::vector<int32_t> lvl_start(nlevel + 1, 0), lvl_body;
+  for (int lv = 0; lv < nlevel; ++lv) {
+    lvl_start[lv] = int(lvl_body.size());
+    for (int i = 0; i < nbody; ++i) if (depth[i] == lv) lvl_body.push_back(i);
+  }
+  lvl_start[nlevel] = int(lvl_body.size());
+  m.nlevel = nlevel;
+  std::vector<int32_t> child_start(nbody + 1, 0), child;
+  for (int i = 0; i < nbody; ++i) {
+    child_start[i] = int(child.size());
+    for (int c = 1; c < nbody; ++c) if (body_parent[c] == i) child.push_back(c);
+  }
+  child_start[nbody] = int(child.size());
+
+  // ---- moving tree
+  int tree_root = -1;
+  for (int d = 0; d < nv; ++d) {
+    int r = body_rootid[dof_bodyid[d]];
+    if (tree_root < 0) tree_root = r;
+    if (r != tree_root) throw std::runtime_error("a single kinematic tree is supported");
+  }
+  m.tree_root = tree_root;
+  auto body_mass = b.f32("body_mass");
+  std::vector<float> tree_mass_v(nbody, 0.f);
+  float tm = 0.f;
+  for (int i = 0; i < nbody; ++i)
+    if (body_rootid[i] == tree_root) { tree_mass_v[i] = body_mass[i]; tm += body_mass[i]; }
+  m.tree_mass = tm;
+
+  // ---- sparse inertia rows
+  std::vector<int32_t> dof_madr(nv), dof_depth(nv);
+  std::vector<uint8_t> m_anc, m_row, m_col;
+  int maxdepth = 0;
+  for (int i = 0; i < nv; ++i) {
+    dof_madr[i] = int(m_anc.size());
+    int c = 0;
+    for (int j = i; j >= 0; j = dof_parentid[j]) { m_anc.push_back(uint8_t(j)); m_row.push_back(uint8_t(i)); m_col.push_back(uint8_t(j)); ++c; }
+    dof_depth[i] = c - 1;
+    maxdepth = std::max(maxdepth, c - 1);
+  }
+  m.nM = int(m_anc.size());
+  m.maxdepth = maxdepth;
+  if (m.nM > 65535) throw std::runtime_error("sparse inertia too large");
+  std::vector<uint8_t> tri_a, tri_b;  // pair p = b(b+1)/2 + a, 0 <= a <= b < maxdepth
+  for (int bb = 0; bb < maxdepth; ++bb) for (int a = 0; a <= bb; ++a) { tri_a.push_back(uint8_t(a)); tri_b.push_back(uint8_t(bb)); }
+  std::vector<int32_t> desc_start(nv + 1, 0);
+  std::vector<uint8_t> desc_dof;
+  std::vector<uint16_t> desc_off;
+  for (int j = 0; j < nv; ++j) {
+    desc_start[j] = int(desc_dof.size());
+    for (int i = j + 1; i < nv; ++i)
+      for (int a = 1; a <= dof_depth[i]; ++a)
+        if (m_anc[dof_madr[i] + a] == j) { desc_dof.push_back(uint8_t(i)); desc_off.push_back(uint16_t(dof_madr[i] + a)); }
+  }
+  desc_start[nv] = int(desc_dof.size());
+
+  // ---- per dof helpers
+  std::vector<int32_t> dof_qadr(nv, -1), dof_limit(nv, -1);
+  for (int j = 0; j < njnt; ++j) if (jnt_type[j] == kJntHinge) dof_qadr[jnt_dofadr[j]] = jnt_qposadr[j];
+
+  // ---- limits
+  auto jnt_range = b.f32("jnt_range"), jnt_margin = b.f32("jnt_margin"), jnt_solref = b.f32("jnt_solref"),
+       jnt_solimp = b.f32("jnt_solimp"), dof_invweight0 = b.f32("dof_invweight0");
+  auto kb = [&](const float* solref, const float* solimp, float* out /* k b dmin dmax width mid power */) {
+    float timeconst = std::max(solref[0], 2.f * m.dt), dampratio = solref[1];
+    float dmin = std::min(std::max(solimp[0], 0.0001f), 0.9999f), dmax = std::min(std::max(solimp[1], 0.0001f), 0.9999f);
+    float width = std::max(1e-15f, solimp[2]), mid = std::min(std::max(solimp[3], 0.0001f), 0.9999f);
+    float power = std::max(1.f, solimp[4]);
+    float k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio), bb = 2.f / (dmax * timeconst);
+    if (solref[0] <= 0) k = -solref[0] / (dmax * dmax);
+    if (solref[1] <= 0) bb = -solref[1] / dmax;
+    out[0] = k; out[1] = bb; out[2] = dmin; out[3] = dmax; out[4] = width; out[5] = mid; out[6] = power;
+  };
+  std::vector<int32_t> lim_dof, lim_qadr;
+  std::vector<float> lim_par;
+  for (int j = 0; j < njnt; ++j) {
+    if (!jnt_limited[j] || jnt_type[j] != kJntHinge) continue;
+    dof_limit[jnt_dofadr[j]] = int(lim_dof.size());
+    lim_dof.push_back(jnt_dofadr[j]);
+    lim_qadr.push_back(jnt_qposadr[j]);
+    float p[12] = {jnt_range[j * 2], jnt_range[j * 2 + 1], jnt_margin[j], dof_invweight0[jnt_dofadr[j]]};
+    kb(&jnt_solref[j * 2], &jnt_solimp[j * 5], p + 4);
+    lim_par.insert(lim_par.end(), p, p + 12);
+  }
+  m.nlimit = int(lim_dof.size());
+  if (m.nlimit > 32 * kLimSlots) throw std::runtime_error("more than 96 joint limits unsupported");
+  if (m.nlimit + 4 * m.ncon != m.nefc) throw std::runtime_error("nefc mismatch");
+
+  // ---- actuators
+  auto act_moment = b.f32("actuator_moment"), act_gain = b.f32("actuator_gain"), act_biasprm = b.f32("actuator_biasprm"),
+       act_dynprm = b.f32("actuator_dynprm"), act_ctrlrange = b.f32("actuator_ctrlrange"),
+       act_forcerange = b.f32("actuator_forcerange");
+  auto act_ctrllimited = b.i32("actuator_ctrllimited"), act_forcelimited = b.i32("actuator_forcelimited"),
+       act_affine = b.i32("actuator_bias_affine"), act_filter = b.i32("actuator_dyn_filter");
+  std::vector<float> a_lo(nu), a_hi(nu), a_dyninv(nu), a_flo(nu), a_fhi(nu);
+  std::vector<int32_t> a_flags(nu);
+  for (int u = 0; u < nu; ++u) {
+    a_lo[u] = act_ctrlrange[u * 2]; a_hi[u] = act_ctrlrange[u * 2 + 1];
+    a_flo[u] = act_forcerange[u * 2]; a_fhi[u] = act_forcerange[u * 2 + 1];
+    a_dyninv[u] = std::max(act_dynprm[u], 1e-15f);  // the kernel divides, like MJX
+    a_flags[u] = (act_ctrllimited[u] ? 1 : 0) | (act_filter[u] ? 2 : 0) | (act_affine[u] ? 4 : 0) | (act_forcelimited[u] ? 8 : 0);
+    for (int d = 0; d < 6 && d < nv; ++d)
+      if (act_moment[size_t(u) * nv + d] != 0.f) throw std::runtime_error("actuators on the free joint unsupported");
+  }
+  std::vector<int32_t> dof_act_start(nv + 1, 0), dof_act_id, act_mom_start(nu + 1, 0), act_mom_dof;
+  std::vector<float> dof_act_coef, act_mom_coef;
+  for (int d = 0; d < nv; ++d) {
+    dof_act_start[d] = int(dof_act_id.size());
+    for (int u = 0; u < nu; ++u)
+      if (act_moment[size_t(u) * nv + d] != 0.f) { dof_act_id.push_back(u); dof_act_coef.push_back(act_moment[size_t(u) * nv + d]); }
+  }
+  dof_act_start[nv] = int(dof_act_id.size());
+  for (int u = 0; u < nu; ++u) {
+    act_mom_start[u] = int(act_mom_dof.size());
+    for (int d = 0; d < nv; ++d)
+      if (act_moment[size_t(u) * nv + d] != 0.f) { act_mom_dof.push_back(d); act_mom_coef.push_back(act_moment[size_t(u) * nv + d]); }
+  }
+  act_mom_start[nu] = int(act_mom_dof.size());
+
+  // ---- contacts
+  auto cg_type = b.i32("cgeom_type"), cg_body = b.i32("cgeom_bodyid"), pair_cgeom = b.i32("pair_cgeom");
+  auto pair_friction = b.f32("pair_friction"), pair_solref = b.f32("pair_solref"), pair_solimp = b.f32("pair_solimp"),
+       pair_margin = b.f32("pair_includemargin"), body_invweight0 = b.f32("body_invweight0"), plane = b.f32("plane");
+  const int plane_body = b.i32("plane_bodyid")[0];
+  for (int k = 0; k < 3; ++k) { m.plane_pos[k] = plane[k]; m.plane_n[k] = plane[3 + k]; }
+  std::vector<int32_t> cb_body, cg_cb(m.ncg);
+  for (int g = 0; g < m.ncg; ++g) {
+    int slot = -1;
+    for (size_t s = 0; s < cb_body.size(); ++s) if (cb_body[s] == cg_body[g]) slot = int(s);
+    if (slot < 0) { slot = int(cb_body.size()); cb_body.push_back(cg_body[g]); }
+    cg_cb[g] = slot;
+  }
+  m.ncb = int(cb_body.size());
+  std::vector<int32_t> con_geom, con_side, con_cb;
+  std::vector<float> con_par;
+  for (size_t p = 0; p < pair_cgeom.size(); ++p) {
+    const int g = pair_cgeom[p];
+    const int n = cg_type[g] == kGeomCapsule ? 2 : 1;
+    const float mu = pair_friction[p * 5];
+    if (pair_friction[p * 5 + 1] != mu) throw std::runtime_error("anisotropic tangential friction unsupported");
+    const float tw = body_invweight0[plane_body * 2] + body_invweight0[cg_body[g] * 2];
+    for (int s = 0; s < n; ++s) {
+      con_geom.push_back(g);
+      con_side.push_back(n == 2 ? (s == 0 ? 1 : -1) : 0);
+      con_cb.push_back(cg_cb[g]);
+      float q[12] = {mu, (tw + mu * mu * tw) * 2.f * mu * mu / m.impratio};
+      kb(&pair_solref[p * 2], &pair_solimp[p * 5], q + 2);
+      q[9] = pair_margin[p];
+      q[10] = q[11] = 0.f;
+      con_par.insert(con_par.end(), q, q + 12);
+    }
+  }
+  if (int(con_geom.size()) != m.ncon) throw std::runtime_error("ncon mismatch");
+  std::vector<int32_t> cb_chain_start(m.ncb + 1, 0), cb_chain_dof, dof_cb_start(nv + 1, 0), dof_cb, cb_con_start(m.ncb + 1, 0), cb_con;
+  std::vector<std::vector<int>> dof_cb_l(nv);
+  for (int s = 0; s < m.ncb; ++s) {
+    cb_chain_start[s] = int(cb_chain_dof.size());
+    int bb = cb_body[s];
+    while (bb > 0 && body_dofnum[bb] == 0) bb = body_parent[bb];
+    std::vector<int> chain;
+    if (bb > 0)
+      for (int i = body_dofadr[bb] + body_dofnum[bb] - 1; i >= 0; i = dof_parentid[i]) chain.push_back(i);
+    for (auto it = chain.rbegin(); it != chain.rend(); ++it) { cb_chain_dof.push_back(*it); dof_cb_l[*it].push_back(s); }
+    cb_con_start[s] = int(cb_con.size());
+    for (int c = 0; c < m.ncon; ++c) if (con_cb[c] == s) cb_con.push_back(c);
+  }
+  cb_chain_start[m.ncb] = int(cb_chain_dof.size());
+  cb_con_start[m.ncb] = int(cb_con.size());
+  for (int d = 0; d < nv; ++d) {
+    dof_cb_start[d] = int(dof_cb.size());
+    for (int s : dof_cb_l[d]) dof_cb.push_back(s);
+  }
+  dof_cb_start[nv] = int(dof_cb.size());
+
+  // ---- per joint floats
+  auto qpos0 = b.f32("qpos0"), qpos_spring = b.f32("qpos_spring");
+  std::vector<float> jnt_qpos0(njnt), jnt_springref(njnt);
+  for (int j = 0; j < njnt; ++j) { jnt_qpos0[j] = qpos0[jnt_qposadr[j]]; jnt_springref[j] = qpos_spring[jnt_qposadr[j]]; }
+
+  // ---- pools (pointer members hold offsets for now)
+#define PI(field, vec) m.field = TMJX_OFF(int, push(t.i32, vec))
+#define PF(field, vec) m.field = TMJX_OFF(float, push(t.f32, vec))
+#define P8(field, vec) m.field = TMJX_OFF(uint8_t, push(t.u8, vec))
+  PI(body_parent, body_parent); PI(body_jntadr, body_jntadr); PI(body_jntnum, body_jntnum); PI(body_dofadr, body_dofadr);
+  PI(body_dofnum, body_dofnum); PI(lvl_start, lvl_start); PI(lvl_body, lvl_body); PI(child_start, child_start); PI(child, child);
+  PF(body_pos, b.f32("body_pos")); PF(body_quat, b.f32("body_quat")); PF(body_ipos, b.f32("body_ipos"));
+  PF(body_iquat, b.f32("body_iquat")); PF(body_inertia, b.f32("body_inertia")); PF(body_mass, body_mass);
+  PF(body_tree_mass, tree_mass_v);
+  PI(jnt_type, jnt_type); PI(jnt_qposadr, jnt_qposadr); PI(jnt_dofadr, jnt_dofadr); PI(jnt_body, jnt_bodyid);
+  PF(jnt_pos, b.f32("jnt_pos")); PF(jnt_axis, b.f32("jnt_axis")); PF(jnt_stiffness, b.f32("jnt_stiffness"));
+  PF(jnt_qpos0, jnt_qpos0); PF(jnt_springref, jnt_springref);
+  PI(dof_body, dof_bodyid); PI(dof_jnt, dof_jntid); PI(dof_madr, dof_madr); PI(dof_depth, dof_depth); PI(dof_limit, dof_limit);
+  PI(dof_qadr, dof_qadr);
+  PF(dof_armature, b.f32("dof_armature")); PF(dof_damping, b.f32("dof_damping"));
+  P8(m_anc, m_anc); P8(m_row, m_row); P8(m_col, m_col); P8(tri_a, tri_a); P8(tri_b, tri_b);
+  PI(desc_start, desc_start); P8(desc_dof, desc_dof);
+  m.desc_off = TMJX_OFF(uint16_t, push(t.u16, desc_off));
+  PF(act_gain, act_gain); PF(act_ctrl_lo, a_lo); PF(act_ctrl_hi, a_hi); PF(act_dyn_inv, a_dyninv); PF(act_bias, act_biasprm);
+  PF(act_force_lo, a_flo); PF(act_force_hi, a_fhi); PI(act_flags, a_flags);
+  PI(dof_act_start, dof_act_start); PI(dof_act_id, dof_act_id); PF(dof_act_coef, dof_act_coef);
+  PI(act_mom_start, act_mom_start); PI(act_mom_dof, act_mom_dof); PF(act_mom_coef, act_mom_coef);
+  PI(lim_dof, lim_dof); PI(lim_qadr, lim_qadr); PF(lim_par, lim_par);
+  PI(cg_type, cg_type); PI(cg_body, cg_body); PI(cg_cb, cg_cb);
+  PF(cg_pos, b.f32("cgeom_pos")); PF(cg_quat, b.f32("cgeom_quat")); PF(cg_size, b.f32("cgeom_size"));
+  PI(con_geom, con_geom); PI(con_side, con_side); PI(con_cb, con_cb); PF(con_par, con_par);
+  PI(cb_body, cb_body); PI(cb_chain_start, cb_chain_start); PI(cb_chain_dof, cb_chain_dof); PI(dof_cb_start, dof_cb_start);
+  PI(dof_cb, dof_cb); PI(cb_con_start, cb_con_start); PI(cb_con, cb_con);
+#undef PI
+#undef PF
+#undef P8
+
+  // ---- shared-memory layout
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += pad4(n); return r; };
+  m.o_qpos = take(m.nq); m.o_qvel = take(nv); m.o_act = take(std::max(m.na, 1)); m.o_ctrl = take(nu); m.o_warm = take(nv);
+  m.o_xpos = take(nbody * 3); m.o_xquat = take(nbody * 4); m.o_cdof = take(nv * 6);
+  m.o_cin = o;
+  {
+    int c = 0;
+    auto tk = [&](int n) { int r = c; c += pad4(n); return r; };
+    m.c_sx = tk(nv); m.c_sy = tk(nv); m.c_sD = tk(nv); m.c_sV = tk(m.ncb * 6); m.c_sW = tk(m.ncon * 6); m.c_sWb = tk(m.ncb * 6);
+    m.c_off = tk(m.ncon * 3); m.c_t1 = tk(m.ncon * 3); m.c_lf = tk(m.nlimit);
+    m.c_end = c;
+    o += std::max(pad4(nbody * 10), c);
+  }
+  m.o_big = o;
+  m.nMpad = pad4(m.nM);
+  {
+    int a = 0;
+    auto tk = [&](int n) { int r = a; a += pad4(n); return r; };
+    m.a_xipos = tk(nbody * 3); m.a_anchor = tk(njnt * 3); m.a_axis = tk(njnt * 3); m.a_cvel = tk(nbody * 6);
+    m.a_cdofdot = tk(nv * 6); m.a_cacc = tk(nbody * 6); m.a_force = tk(nu);
+    if (pad4(nv * 6) > m.nMpad) throw std::runtime_error("M-build scratch does not fit");
+    o += std::max(a, 2 * m.nMpad);
+  }
+  m.smem_floats = o;
+}
+
+/* Turn the offsets stored in the pointer members into device pointers. */
+inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint8_t* d8, const float* df) {
+#define RI(f) m.f = di + reinterpret_cast<uintptr_t>(m.f)
+#define RF(f) m.f = df + reinterpret_cast<uintptr_t>(m.f)
+#define R8(f) m.f = d8 + reinterpret_cast<uintptr_t>(m.f)
+  RI(body_parent); RI(body_jntadr); RI(body_jntnum); RI(body_dofadr); RI(body_dofnum); RI(lvl_start); RI(lvl_body);
+  RI(child_start); RI(child);
+  RF(body_pos); RF(body_quat); RF(body_ipos); RF(body_iquat); RF(body_inertia); RF(body_mass); RF(body_tree_mass);
+  RI(jnt_type); RI(jnt_qposadr); RI(jnt_dofadr); RI(jnt_body);
+  RF(jnt_pos); RF(jnt_axis); RF(jnt_stiffness); RF(jnt_qpos0); RF(jnt_springref);
+  RI(dof_body); RI(dof_jnt); RI(dof_madr); RI(dof_depth); RI(dof_limit); RI(dof_qadr);
+  RF(dof_armature); RF(dof_damping);
+  R8(m_anc); R8(m_row); R8(m_col); R8(tri_a); R8(tri_b);
+  RI(desc_start); R8(desc_dof);
+  m.desc_off = d16 + reinterpret_cast<uintptr_t>(m.desc_off);
+  RF(act_gain); RF(act_ctrl_lo); RF(act_ctrl_hi); RF(act_dyn_inv); RF(act_bias); RF(act_force_lo); RF(act_force_hi);
+  RI(act_flags); RI(dof_act_start); RI(dof_act_id); RF(dof_act_coef); RI(act_mom_start); RI(act_mom_dof); RF(act_mom_coef);
+  RI(lim_dof); RI(lim_qadr); RF(lim_par);
+  RI(cg_type); RI(cg_body); RI(cg_cb); RF(cg_pos); RF(cg_quat); RF(cg_size);
+  RI(con_geom); RI(con_side); RI(con_cb); RF(con_par);
+  RI(cb_body); RI(cb_chain_start); RI(cb_chain_dof); RI(dof_cb_start); RI(dof_cb); RI(cb_con_start); RI(cb_con);
+#undef RI
+#undef RF
+#undef R8
+}
+
+/* Task constants: obs sizes, packed clip-frame layout (the subset of ReferenceClip the step reads). */
+inline void build_task(const DevModel& m, const TmjxTaskConfig& cfg, int n_ref_bodies, DevTask& t) {
+  t.cfg = cfg;
+  const int nj = m.nq - 7;
+  t.ref_obs_size = cfg.traj_length * (3 + 4 + cfg.n_joint_idxs + 3 * cfg.n_body_idxs);
+  t.prop_obs_size = (m.nq - 7) + (m.nv - 6) + m.nv + 1 + 3 + 3 * cfg.n_appendages;
+  t.obs_size = t.ref_obs_size + t.prop_obs_size;
+  std::vector<int> rows;
+  auto slot_of = [&](int id) {
+    const int row = std::min(std::max(id, 0), n_ref_bodies - 1);  // jnp gather clamps
+    for (size_t s = 0; s < rows.size(); ++s) if (rows[s] == row) return int(s);
+    rows.push_back(row);
+    return int(rows.size()) - 1;
+  };
+  for (int i = 0; i < cfg.n_body_idxs; ++i) { t.body_slot[i] = slot_of(cfg.body_idxs[i]); t.body_row[i] = rows[t.body_slot[i]]; }
+  for (int i = 0; i < cfg.n_endeff_idxs; ++i) { t.endeff_slot[i] = slot_of(cfg.endeff_idxs[i]); t.endeff_row[i] = rows[t.endeff_slot[i]]; }
+  for (int i = 0; i < cfg.n_joint_idxs; ++i) {
+    int col = cfg.joint_idxs[i] - 1;
+    if (col < 0) col += nj;
+    t.joint_col[i] = std::min(std::max(col, 0), nj - 1);
+  }
+  t.n_rows = int(rows.size());
+  t.o_pos = 0; t.o_quat = 4; t.o_angvel = 8; t.o_joints = 12; t.o_bodies = 12 + detail::pad4(nj);
+  t.frame_stride = detail::pad4(t.o_bodies + 3 * t.n_rows);
+}
+inline std::vector<int> task_rows(const DevTask& t) {
+  std::vector<int> rows(t.n_rows, 0);
+  for (int i = 0; i < t.cfg.n_body_idxs; ++i) rows[t.body_slot[i]] = t.body_row[i];
+  for (int i = 0; i < t.cfg.n_endeff_idxs; ++i) rows[t.endeff_slot[i]] = t.endeff_row[i];
+  return rows;
+}
+
+}  // namespace tmjx
+#endif  // TMJX_TABLES_H_

@@ -1,0 +1,275 @@
+"""Brax-style `Env` mirror of the reference tracking env, backed by the B200 step library.
+
+Drop-in surface (names, argument meaning and conventions follow the reference):
+  * `MultiClipTracking(reference_clip, walker, reward_config, physics_steps_per_control_step, ...)`
+        reference track_mjx/environment/task/multi_clip_tracking.py:13-109
+  * `.reset(rng[, clip_idx]) -> State`, `.reset_from_clip(rng, info, noise=True) -> State`,
+    `.step(state, action) -> State`      reference .../task/single_clip_tracking.py:121-320
+  * `State(pipeline_state, obs, reward, done, metrics, info)`   (brax.envs.base.State)
+  * `wrap(env, episode_length)`: EpisodeWrapper + auto-reset fused into the same launch
+        reference track_mjx/environment/wrappers.py:18-56, 104-144, 288-310
+
+Differences that are inherent to leaving JAX (documented in DESIGN.md): the env is *batched* (the leading
+axis of every array is the env axis that `jax.vmap` would add), arrays are `torch` CUDA tensors, `rng` is a
+`torch.Generator` or an int seed (threefry parity is not claimed), and `State` objects returned by `step`
+share the env's device buffers (the functional-purity of the JAX original is traded for zero-copy stepping;
+`State.clone()` gives an independent copy).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import config as _config
+from .clips import ReferenceClip
+
+
+@dataclasses.dataclass
+class PipelineState:
+    """The slice of `mjx.Data` the task reads and carries (lazily the rest is not materialised)."""
+
+    qpos: torch.Tensor
+    qvel: torch.Tensor
+    act: torch.Tensor
+    time: torch.Tensor
+    qacc_warmstart: torch.Tensor
+    xpos: torch.Tensor
+    xquat: torch.Tensor
+    qfrc_actuator: torch.Tensor
+
+    # brax aliases
+    @property
+    def q(self):
+        return self.qpos
+
+    @property
+    def qd(self):
+        return self.qvel
+
+
+@dataclasses.dataclass
+class State:
+    pipeline_state: PipelineState
+    obs: torch.Tensor
+    reward: torch.Tensor
+    done: torch.Tensor
+    metrics: dict[str, torch.Tensor]
+    info: dict[str, Any]
+
+    def clone(self) -> "State":
+        cl = lambda x: x.clone() if isinstance(x, torch.Tensor) else x  # noqa: E731
+        ps = PipelineState(**{f.name: cl(getattr(self.pipeline_state, f.name)) for f in dataclasses.fields(PipelineState)})
+        return State(ps, cl(self.obs), cl(self.reward), cl(self.done), {k: cl(v) for k, v in self.metrics.items()},
+                     {k: cl(v) for k, v in self.info.items()})
+
+
+class Stepper:
+    """Owns the device model, clip table and per-env buffers; thin wrapper over the C ABI."""
+
+    def __init__(self, blob: bytes, cfg: _config.TaskConfigC, clips: ReferenceClip, n_env: int, device: int | torch.device = 0,
+                 debug: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("track_mjx_b200 needs a CUDA device: the env step has no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else device
+        self.n_env = n_env
+        self.cfg = cfg
+        self._model = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.tmjx_model_create(blob, len(blob), C.byref(cfg), self.device.index, C.byref(self._model)),
+                    "tmjx_model_create")
+            d = L.DimsC()
+            L.check(self.lib, self.lib.tmjx_model_dims(self._model, C.byref(d)), "tmjx_model_dims")
+            self.dims = L.dims_dict(d)
+            fp = C.POINTER(C.c_float)
+            arrs = [np.ascontiguousarray(getattr(clips, k), np.float32) for k in (
+                "position", "quaternion", "joints", "body_positions", "velocity", "angular_velocity", "joints_velocity",
+                "body_quaternions")]
+            self._clips = C.c_void_p()
+            L.check(self.lib, self.lib.tmjx_clips_create(
+                self._model, *[a.ctypes.data_as(fp) for a in arrs], clips.position.shape[0], clips.position.shape[1],
+                clips.body_positions.shape[2], C.byref(self._clips)), "tmjx_clips_create")
+        self.n_clips, self.clip_length = clips.position.shape[:2]
+        self.buf: dict[str, torch.Tensor] = {}
+        fields = L.STATE_FIELDS + L.OUT_FIELDS + (tuple(f for f in L.DEBUG_FIELDS if f[0] != "dbg_qM") if debug else ())
+        for name, spec, kind in fields:
+            self.buf[name] = torch.zeros((n_env, L.field_size(spec, self.dims)), device=self.device,
+                                         dtype=torch.float32 if kind == "f" else torch.int32)
+        self._state_c = L.fill_struct(L.StateC(), L.STATE_FIELDS, self.buf, lambda t: t.data_ptr())
+        self._out_c = L.fill_struct(L.OutC(), L.OUT_FIELDS + L.DEBUG_FIELDS, self.buf, lambda t: t.data_ptr())
+
+    def close(self):
+        if getattr(self, "_clips", None):
+            self.lib.tmjx_clips_destroy(self._clips)
+            self._clips = None
+        if getattr(self, "_model", None):
+            self.lib.tmjx_model_destroy(self._model)
+            self._model = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, flags: int = 0):
+        L.check(self.lib, self.lib.tmjx_forward(self._model, self._clips, C.byref(self._state_c), C.byref(self._out_c),
+                                                self.n_env, flags, self._stream()), "tmjx_forward")
+
+    def step(self, action: torch.Tensor, flags: int = 0):
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(self.device, torch.float32).contiguous()
+        if action.shape != (self.n_env, self.dims["nu"]):
+            raise ValueError(f"action must have shape ({self.n_env}, {self.dims['nu']})")
+        L.check(self.lib, self.lib.tmjx_step(self._model, self._clips, C.c_void_p(action.data_ptr()), C.byref(self._state_c),
+                                             C.byref(self._out_c), self.n_env, flags, self._stream()), "tmjx_step")
+
+    def clips_device_bytes(self) -> int:
+        return int(self.lib.tmjx_clips_device_bytes(self._clips))
+
+    def fp32_peak_tflops(self) -> float:
+        return float(self.lib.tmjx_fp32_peak_tflops(self.device.index, self._stream()))
+
+
+class MultiClipTracking:
+    """Batched multi-clip tracking env (reference multi_clip_tracking.py:13; single-clip = a 1-clip table)."""
+
+    def __init__(
+        self,
+        reference_clip: ReferenceClip,
+        walker,
+        reward_config: _config.RewardConfig | None,
+        physics_steps_per_control_step: int,
+        reset_noise_scale: float,
+        solver: str = "cg",
+        iterations: int = 4,
+        ls_iterations: int = 4,
+        mj_model_timestep: float = 0.002,
+        mocap_hz: int = 50,
+        clip_length: int = 250,
+        random_init_range: int = 50,
+        traj_length: int = 5,
+        *,
+        num_envs: int,
+        device: int = 0,
+        debug: bool = False,
+    ):
+        self.walker = walker
+        self._reward_config = reward_config or _config.RewardConfig()
+        self._reference_clips = reference_clip
+        self._n_clips = reference_clip.position.shape[0]
+        self._reset_noise_scale = reset_noise_scale
+        self._mocap_hz = mocap_hz
+        self._ref_len = traj_length
+        self._steps_for_cur_frame = (1.0 / (mocap_hz * mj_model_timestep)) / physics_steps_per_control_step
+        self._n_frames = physics_steps_per_control_step
+        self.cfg = _config.make_task_config(
+            walker, self._reward_config, physics_steps_per_control_step=physics_steps_per_control_step, solver=solver,
+            iterations=iterations, ls_iterations=ls_iterations, mj_model_timestep=mj_model_timestep, mocap_hz=mocap_hz,
+            clip_length=clip_length, random_init_range=random_init_range, traj_length=traj_length)
+        self.num_envs = num_envs
+        self.stepper = Stepper(walker.blob, self.cfg, reference_clip, num_envs, device, debug=debug)
+        self.device = self.stepper.device
+        self._clip_pos = torch.from_numpy(np.ascontiguousarray(reference_clip.position)).to(self.device)
+        self._clip_quat = torch.from_numpy(np.ascontiguousarray(reference_clip.quaternion)).to(self.device)
+        self._clip_joints = torch.from_numpy(np.ascontiguousarray(reference_clip.joints)).to(self.device)
+        self._autoreset = False
+
+    # ---- attributes callers use
+    @property
+    def dt(self) -> float:
+        return self.cfg.mj_model_timestep * self._n_frames
+
+    @property
+    def action_size(self) -> int:
+        return self.stepper.dims["nu"]
+
+    @property
+    def observation_size(self) -> int:
+        return self.stepper.dims["obs_size"]
+
+    @property
+    def sys(self):
+        return self.walker  # exposes nq / nv / nu like brax `System`
+
+    def _gen(self, rng) -> torch.Generator:
+        if isinstance(rng, torch.Generator):
+            return rng
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(rng))
+        return g
+
+    def reset(self, rng, clip_idx: torch.Tensor | int | None = None) -> State:
+        """reference multi_clip_tracking.py:74-96 (start_frame ~ randint(0, 44), clip_idx ~ randint(0, n_clips))."""
+        g = self._gen(rng)
+        n = self.num_envs
+        start_frame = torch.randint(0, 44, (n,), generator=g, device=self.device, dtype=torch.int32)
+        if clip_idx is None:
+            clip_idx = torch.randint(0, self._n_clips, (n,), generator=g, device=self.device, dtype=torch.int32)
+        elif not isinstance(clip_idx, torch.Tensor):
+            clip_idx = torch.full((n,), int(clip_idx), device=self.device, dtype=torch.int32)
+        info = {"clip_idx": clip_idx.to(torch.int32), "start_frame": start_frame}
+        return self.reset_from_clip(g, info, noise=True)
+
+    def reset_from_clip(self, rng, info: dict[str, Any], noise: bool = True) -> State:
+        """reference single_clip_tracking.py:121-205."""
+        g = self._gen(rng)
+        b = self.stepper.buf
+        n, nq, nv = self.num_envs, self.stepper.dims["nq"], self.stepper.dims["nv"]
+        ci, sf = info["clip_idx"].long(), info["start_frame"].long()
+        new_qpos = torch.cat([self._clip_pos[ci, sf], self._clip_quat[ci, sf], self._clip_joints[ci, sf]], dim=-1)
+        s = self._reset_noise_scale
+        # the reference draws qpos and qvel noise from the SAME key (:153-161): the first nv qvel draws equal the qpos draws
+        u = (torch.rand((n, nq), generator=g, device=self.device) * 2 - 1) * s
+        b["qpos"].copy_(new_qpos + u)
+        b["qvel"].copy_(u[:, :nv] if noise else torch.zeros((n, nv), device=self.device))
+        b["clip_idx"].copy_(info["clip_idx"].view(n, 1))
+        b["start_frame"].copy_(info["start_frame"].view(n, 1))
+        self.stepper.forward(L.TMJX_F_SNAPSHOT if self._autoreset else 0)
+        return self._state()
+
+    def step(self, state: State, action: torch.Tensor) -> State:
+        """reference single_clip_tracking.py:207-320 (+ fused wrappers after `wrap`)."""
+        self.stepper.step(action, L.TMJX_F_AUTORESET if self._autoreset else 0)
+        return self._state()
+
+    def _state(self) -> State:
+        b = self.stepper.buf
+        ps = PipelineState(b["qpos"], b["qvel"], b["act"], b["time"][:, 0], b["qacc_warmstart"],
+                           b["xpos"].view(self.num_envs, -1, 3), b["xquat"].view(self.num_envs, -1, 4), b["qfrc_actuator"])
+        metrics = {k: b["metrics"][:, i] for i, k in enumerate(_config.METRIC_NAMES)}
+        info = {
+            "clip_idx": b["clip_idx"][:, 0], "start_frame": b["start_frame"][:, 0], "prev_ctrl": b["prev_ctrl"],
+            "action_buffer": b["action_buffer"].view(self.num_envs, self.cfg.var_window_size, -1),
+            "buffer_index": b["buffer_index"][:, 0], "cur_frame": b["cur_frame"][:, 0],
+            "reference_obs_size": self.stepper.dims["reference_obs_size"],
+            "proprioceptive_obs_size": self.stepper.dims["proprioceptive_obs_size"],
+        }
+        if self._autoreset:
+            info.update(steps=b["steps"][:, 0], truncation=b["truncation"][:, 0])
+        return State(ps, b["obs"], b["reward"][:, 0], b["done"][:, 0], metrics, info)
+
+    def _get_reference_clip(self, info) -> ReferenceClip:
+        return self._reference_clips
+
+
+def wrap(env: MultiClipTracking, episode_length: int | None = None) -> MultiClipTracking:
+    """reference wrappers.wrap (wrappers.py:18-56): EpisodeWrapper + VmapWrapper + auto-reset.
+
+    The env is already batched, and the episode counter / truncation / `where(done, first_*, cur)` restore are
+    executed inside the step launch (TMJX_F_AUTORESET), so this only switches the fused path on.
+    """
+    if episode_length is not None and int(episode_length) != env.cfg.episode_length:
+        env.cfg.episode_length = int(episode_length)
+        raise ValueError("episode_length is fixed at construction (clip_length - random_init_range - traj_length)")
+    env._autoreset = True
+    return env
