@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: rodent-tracking env-steps/sec (device-timed), BASELINE.json `configs[1]`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one control step of the wrapped tracking env over one batch of 4096 envs per GPU
+(10 physics substeps + reward + termination + observation + fused episode/auto-reset), random N(0,1)
+actions.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+  value     whole-job env-steps/s, actions already resident in HBM, CUDA events around each step launch,
+            L2 flushed between timed iterations, max over ranks;
+  e2e       the same through the Python env API with HOST buffers: every step copies the actions from
+            pinned host memory and reads obs / reward / done back to pinned host memory;
+  roofline  FP32-pipe (the binding roofline of this path) and HBM fractions of the step kernel;
+  cpu_baseline  the CPU oracle (a port of the reference algorithm, `oracle/`) on a bounded sample.
+
+`--impl reference` times the reference's CPU path.  The reference itself (JAX + MuJoCo-MJX + Brax) cannot be
+installed in this image (no wheels, no network), so that arm runs the oracle port on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rodent-tracking env-steps/sec (device-timed)"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 4096
+# algorithmic work per env-step at the default config (formulas in DESIGN.md "Roofline")
+B_ALG = 15348.0            # bytes of unavoidable HBM traffic per env-step
+W_ALG = 3.775e6            # structure-exploiting FLOPs per env-step (10 x 375 kFLOP + 25 kFLOP)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "rodent single-clip tracking, 4096 envs per B200, full step + reward + obs + fused auto-reset, fp32 (BASELINE configs[1])",
+        "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus, "n_clips": 1, "clip_length": 250,
+        "physics_steps_per_control_step": 10, "solver": "cg", "iterations": 5, "ls_iterations": 5,
+        "actions": "N(0,1) per step (clipped to ctrlrange by the actuator model)", "l2": "flushed between timed iterations",
+        "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
+    }
+
+
+def build_env_pieces(n_clips=1):
+    from track_mjx_b200 import clips as clipmod, config
+    from track_mjx_b200.walker import Rodent
+
+    walker = Rodent(torque_actuators=True, rescale_factor=0.9)
+    clips = clipmod.make_synthetic_clips(walker.sections, n_clips)
+    return walker, clips, config
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference algorithm, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    import common
+    from oracle.oracle import Oracle
+
+    walker, clips, config = build_env_pieces(1)
+    env_args = {k: v for k, v in config.DEFAULT_ENV_ARGS.items() if k != "reset_noise_scale"}
+    cfg = config.make_task_config(walker, config.RewardConfig(), **env_args)
+    cores = os.cpu_count() or 1
+    orc = Oracle(walker.blob, cfg, clips, dtype=np.float32, nthreads=cores)
+    sample = min(ENVS_PER_GPU, max(64, 4 * cores))
+    buf = orc.alloc(sample, debug=False)
+    common.put(buf, common.init_buffers(buf, clips, seed=0))
+    from track_mjx_b200 import _lib as L
+
+    orc.forward(buf, L.TMJX_F_SNAPSHOT)
+    rng = np.random.default_rng(42)
+    acts = [rng.normal(size=(sample, walker.nu)).astype(np.float32) for _ in range(args.warmup + args.steps)]
+    for i in range(args.warmup):
+        orc.step(buf, acts[i], L.TMJX_F_AUTORESET)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.step(buf, acts[args.warmup + i], L.TMJX_F_AUTORESET)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} of {ENVS_PER_GPU} envs per step x {args.steps} control steps, fp32 oracle port (dense MJX-style algebra), OpenMP over envs"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference (JAX/MJX/Brax) not installable in this image; this is the CPU oracle port of its algorithm",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    from track_mjx_b200.env import MultiClipTracking, wrap
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    walker, clips, config = build_env_pieces(1)
+    env = wrap(MultiClipTracking(clips, walker, config.RewardConfig(), num_envs=ENVS_PER_GPU, device=local_rank, **config.DEFAULT_ENV_ARGS))
+    state = env.reset(1000 + rank)
+    K, W = args.steps, args.warmup
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    n_act = min(K + W, 64)
+    acts = [torch.randn(ENVS_PER_GPU, env.action_size, device=dev, generator=gen) for _ in range(n_act)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident arm
+    for i in range(W):
+        state = env.step(state, acts[i % n_act])
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    wall0 = time.perf_counter()
+    rew_sum = torch.zeros((), device=dev)
+    done_sum = torch.zeros((), device=dev)
+    for i in range(K):
+        flush.zero_()
+        evs[i][0].record()
+        state = env.step(state, acts[(W + i) % n_act])
+        evs[i][1].record()
+        rew_sum += state.reward.sum()
+        done_sum += state.done.sum()
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    stats = torch.stack([rew_sum, done_sum]).double()
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)   # episode statistics over NVLink (the only collective of the env path)
+    max_ms = float(t.item())
+    value = ENVS_PER_GPU * world * K / (max_ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out, every step
+    obs_dim = env.observation_size
+    h_act = [torch.randn(ENVS_PER_GPU, env.action_size).pin_memory() for _ in range(4)]
+    d_act = torch.empty(ENVS_PER_GPU, env.action_size, device=dev)
+    h_obs = torch.empty(ENVS_PER_GPU, obs_dim).pin_memory()
+    h_rew = torch.empty(ENVS_PER_GPU).pin_memory()
+    h_done = torch.empty(ENVS_PER_GPU).pin_memory()
+
+    def e2e_step(i, st):
+        d_act.copy_(h_act[i % 4], non_blocking=True)
+        st = env.step(st, d_act)
+        h_obs.copy_(st.obs, non_blocking=True)
+        h_rew.copy_(st.reward, non_blocking=True)
+        h_done.copy_(st.done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller needs the host results before the next action
+        return st
+
+    for i in range(W):
+        state = e2e_step(i, state)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        state = e2e_step(i, state)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = ENVS_PER_GPU * world * K / float(te.item())
+    h2d = ENVS_PER_GPU * env.action_size * 4
+    d2h = ENVS_PER_GPU * (obs_dim + 2) * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the step kernel (the only kernel of a step), from the same CUDA-event durations
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fp32_peak = env.stepper.fp32_peak_tflops()   # FMA microbenchmark on this box (no fp32 figure in MEASURED_PEAKS.json)
+    per_gpu_rate = ENVS_PER_GPU * K / (max_ms * 1e-3)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "step_kernel_dram_bytes.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {
+        "bound": "fp32", "achieved": per_gpu_rate * W_ALG / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": per_gpu_rate * W_ALG / 1e12 / fp32_peak if fp32_peak > 0 else None, "traffic": traffic,
+        "peak_source": "measured FP32 FMA microbenchmark (tmjx_fp32_peak_tflops) in this run",
+        "kernel": "tmjx_env_kernel<true>", "kernel_ms": max_ms / K, "algorithmic_flops_per_launch": W_ALG * ENVS_PER_GPU,
+        "algorithmic_bytes_per_launch": B_ALG * ENVS_PER_GPU,
+        "hbm": {"achieved": per_gpu_rate * B_ALG / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu_rate * B_ALG / 1e9 / hbm_peak,
+                "peak_source": hbm_src},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_leg(walker, clips, config)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world), "clocks": clocks, "gpu_launches": K,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "wall_s_timed_region": wall,
+        "episode_stats": {"mean_reward": float(stats[0].item()) / (ENVS_PER_GPU * world * K), "done_frac": float(stats[1].item()) / (ENVS_PER_GPU * world * K)},
+    }
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg(walker, clips, config):
+    """The oracle port on the host cores of this box, bounded to ~10-20 s."""
+    import numpy as np
+
+    import common
+    from oracle.oracle import Oracle
+    from track_mjx_b200 import _lib as L
+
+    env_args = {k: v for k, v in config.DEFAULT_ENV_ARGS.items() if k != "reset_noise_scale"}
+    cfg = config.make_task_config(walker, config.RewardConfig(), **env_args)
+    cores = os.cpu_count() or 1
+    orc = Oracle(walker.blob, cfg, clips, dtype=np.float32, nthreads=cores)
+    sample = min(ENVS_PER_GPU, max(64, 4 * cores))
+    buf = orc.alloc(sample, debug=False)
+    common.put(buf, common.init_buffers(buf, clips, seed=0))
+    orc.forward(buf, L.TMJX_F_SNAPSHOT)
+    rng = np.random.default_rng(42)
+    orc.step(buf, rng.normal(size=(sample, walker.nu)).astype(np.float32), L.TMJX_F_AUTORESET)
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < 10.0 and steps < 50:
+        orc.step(buf, rng.normal(size=(sample, walker.nu)).astype(np.float32), L.TMJX_F_AUTORESET)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} of {ENVS_PER_GPU} envs x {steps} control steps, fp32 CPU oracle (port of the MJX algorithm, dense), OpenMP over envs"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

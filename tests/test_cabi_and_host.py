@@ -1,0 +1,85 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/tmjx.h declares, struct layouts
+agree between ctypes and C, blob round-trips, index tables, config arithmetic (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from track_mjx_b200 import _lib as L
+from track_mjx_b200 import clips as clipmod, config, model_blob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    ge.build()
+    header = open(os.path.join(ROOT, "include", "tmjx.h")).read()
+    declared = set(re.findall(r"\b(tmjx_[a-z0-9_]+)\s*\(", header))
+    assert {"tmjx_step", "tmjx_forward", "tmjx_model_create", "tmjx_clips_create"} <= declared
+    lib = C.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tmjx_abi_version() == config.TMJX_ABI_VERSION
+
+
+def test_struct_layouts_match_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "tmjx.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(TmjxTaskConfig), '
+                   'sizeof(TmjxState), sizeof(TmjxOut), sizeof(TmjxDims), __builtin_offsetof(TmjxTaskConfig, torso_idx));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(config.TaskConfigC), C.sizeof(L.StateC), C.sizeof(L.OutC), C.sizeof(L.DimsC),
+                     config.TaskConfigC.torso_idx.offset]
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libtmjx.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        L.load()
+
+
+def test_blob_roundtrip_and_dims(walker):
+    sec = model_blob.unpack(walker.blob)
+    again = model_blob.unpack(model_blob.pack_sections(sec))
+    assert sec.keys() == again.keys()
+    for k in sec:
+        assert (sec[k] == again[k]).all()
+    assert (walker.nq, walker.nv, walker.nu, walker.na, walker.nbody, walker.njnt) == (74, 73, 38, 38, 68, 68)
+    assert (walker.ncon, walker.nefc) == (30, 187)
+    assert abs(float(sec["opt"][0]) - 0.002) < 1e-9
+
+
+def test_walker_index_tables(walker):
+    """SURVEY A.4 (mj_name2id equivalents for rodent-full-clips.yaml's name lists)."""
+    assert list(walker.joint_idxs) == [1, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 33, 47, 48, 50, 51, 52, 53, 54, 55, 56, 57,
+                                       58, 60, 61, 62, 63, 64, 65, 66, 67]
+    assert list(walker.body_idxs) == [3, 10, 11, 12, 13, 15, 16, 17, 56, 57, 58, 59, 60, 62, 63, 64, 65, 67]
+    assert list(walker.endeff_idxs) == [13, 17, 61, 66, 56]
+    assert walker.torso_idx == 3
+
+
+def test_task_config_arithmetic(task_cfg):
+    assert task_cfg.episode_length == 195                      # train.py:221-225 with the shipped yaml
+    assert task_cfg.n_joint_idxs == 33 and task_cfg.n_body_idxs == 18 and task_cfg.n_endeff_idxs == 5
+    assert abs(task_cfg.var_coeff - 5e-3) < 1e-9               # yaml overrides the dataclass default (quirk 11)
+
+
+def test_synthetic_clip_shapes(walker, clips2):
+    c = clips2
+    assert c.position.shape == (2, 250, 3) and c.quaternion.shape == (2, 250, 4) and c.joints.shape == (2, 250, 67)
+    assert c.body_positions.shape == (2, 250, 67, 3) and c.body_quaternions.shape == (2, 250, 67, 4)
+    assert c.velocity.shape == (2, 250, 3) and c.angular_velocity.shape == (2, 250, 3) and c.joints_velocity.shape == (2, 250, 67)
+    assert np.allclose(np.linalg.norm(c.quaternion, axis=-1), 1, atol=1e-6)
+    lo, hi = walker.sections["jnt_range"].reshape(-1, 2)[1:].T
+    assert (c.joints >= lo - 1e-6).all() and (c.joints <= hi + 1e-6).all()
+    # row 0 is the world body, row 1 the walker root (floor removed): stac-mjx layout
+    assert np.allclose(c.body_positions[:, :, 0], 0) and np.allclose(c.body_positions[:, :, 1], c.position, atol=1e-6)
+    again = clipmod.make_synthetic_clips(walker.sections, 2)
+    assert (again.joints == c.joints).all()

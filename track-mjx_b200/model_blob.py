@@ -121,3 +121,42 @@ def unpack(blob: bytes) -> dict[str, np.ndarray]:
         name = name.split(b"\0")[0].decode()
         out[name] = np.frombuffer(blob, np.float32 if dt == 0 else np.int32, count, off).copy()
     return out
+
+
+def pack_sections(sec: dict[str, np.ndarray]) -> bytes:
+    """Re-pack an (edited) dict of sections as returned by `unpack` (tests use this to build model variants)."""
+    names = list(sec)
+    dir_size = 16 + 40 * len(names)
+    off = (dir_size + 15) // 16 * 16
+    entries, chunks = [], []
+    for n in names:
+        a = np.ascontiguousarray(sec[n])
+        if a.dtype not in (np.float32, np.int32):
+            raise ValueError(f"section {n}: dtype {a.dtype}")
+        raw = a.tobytes()
+        entries.append(struct.pack("<24siiq", n.encode()[:23], 0 if a.dtype == np.float32 else 1, a.size, off))
+        pad = (-len(raw)) % 16
+        chunks.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+    head = struct.pack("<IIii", MAGIC, VERSION, len(names), 0) + b"".join(entries)
+    head += b"\0" * ((-len(head)) % 16)
+    return head + b"".join(chunks)
+
+
+def as_model(sec: dict[str, np.ndarray]) -> dict[str, Any]:
+    """View unpacked sections as the dict `mjcf.kinematics / body_jacobians / mass_matrix` expect (fp64)."""
+    d = sec["dims"]
+    nq, nv, nu, na, nbody, njnt = (int(x) for x in d[:6])
+    f = lambda k, *shape: sec[k].astype(np.float64).reshape(*shape) if shape else sec[k].astype(np.float64)  # noqa: E731
+    i = lambda k: sec[k].astype(int)  # noqa: E731
+    return dict(
+        nq=nq, nv=nv, nu=nu, na=na, nbody=nbody, njnt=njnt,
+        body_parentid=i("body_parentid"), body_rootid=i("body_rootid"), body_jntadr=i("body_jntadr"),
+        body_jntnum=i("body_jntnum"), body_dofadr=i("body_dofadr"), body_dofnum=i("body_dofnum"),
+        jnt_type=i("jnt_type"), jnt_qposadr=i("jnt_qposadr"), jnt_dofadr=i("jnt_dofadr"), jnt_bodyid=i("jnt_bodyid"),
+        dof_bodyid=i("dof_bodyid"), dof_parentid=i("dof_parentid"),
+        body_pos=f("body_pos", nbody, 3), body_quat=f("body_quat", nbody, 4), body_ipos=f("body_ipos", nbody, 3),
+        body_iquat=f("body_iquat", nbody, 4), body_mass=f("body_mass"), body_inertia=f("body_inertia", nbody, 3),
+        jnt_pos=f("jnt_pos", njnt, 3), jnt_axis=f("jnt_axis", njnt, 3), jnt_range=f("jnt_range", njnt, 2),
+        qpos0=f("qpos0"), dof_armature=f("dof_armature"), dof_damping=f("dof_damping"),
+    )
