@@ -43,6 +43,8 @@ enum { kJntFree = 0, kJntHinge = 3 };
 thread_local std::string g_err;
 
 // ------------------------------------------------------------------ small math (mjx/_src/math.py)
+// jnp.minimum / jnp.maximum propagate NaN (std::min / fminf do not)
+template <class T> inline T jmin(T a, T b) { return (a != a || b != b) ? std::numeric_limits<T>::quiet_NaN() : (a < b ? a : b); }
 template <class T> inline T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <class T> inline void cross3(const T* a, const T* b, T* o) {
   T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -1011,7 +1013,7 @@ void run_step(const Sim<T>& s, const void* action_v, TmjxState* st, TmjxOut* o, 
       for (int k = 0; k < 4; ++k) { qs[k] /= ns; qt[k] /= nt; }
     }
     const T qd = qs[0] * qt[0] + qs[1] * qt[1] + qs[2] * qt[2] + qs[3] * qt[3];
-    const T bq = T(0.5) * std::acos(std::min(T(1), T(2) * qd * qd - T(1)));
+    const T bq = T(0.5) * std::acos(jmin(T(1), T(2) * qd * qd - T(1)));
     const T quat_distance = bq * bq;
     const T quat_reward = T(cfg.quat_reward_weight) * std::exp(-T(cfg.quat_reward_exp_scale) * quat_distance);
     T joint_distance = 0;
@@ -1039,7 +1041,7 @@ void run_step(const Sim<T>& s, const void* action_v, TmjxState* st, TmjxOut* o, 
     const T ctrl_diff_cost = T(cfg.ctrl_diff_cost_weight) * ad;
     T en = 0;
     for (int i = 6; i < m.nv; ++i) en += std::abs(d.qvel[i]) * std::abs(d.qfrc_actuator[i]);
-    const T energy_cost = T(cfg.energy_cost_weight) * std::min(en, T(50));
+    const T energy_cost = T(cfg.energy_cost_weight) * jmin(en, T(50));
     const T torso_z = d.xpos[cfg.torso_idx * 3 + 2];
     T healthy = torso_z < T(cfg.healthy_z_min) ? T(0) : T(1);
     if (torso_z > T(cfg.healthy_z_max)) healthy = 0;

@@ -1,0 +1,96 @@
+"""Join an ncu SASS-level source page with nvdisasm line info and aggregate executed instructions / stall samples
+per CUDA source line and per function.
+
+    ncu -i prof.ncu-rep --page source --csv --print-source sass > sass.csv
+    python tools/ncu_hotspots.py sass.csv track-mjx_b200/csrc/libtmjx.so tmjx_env_kernelILb1 [top_n]
+"""
+import csv
+import re
+import subprocess
+import sys
+import tempfile
+from collections import defaultdict
+
+
+def main():
+    sass_csv, so, kern = sys.argv[1:4]
+    import os
+    so = os.path.abspath(so)
+    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
+    import glob
+
+    cubin = glob.glob(tmp + "/*.cubin")[0]
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout.splitlines()
+    addr2line, inside, src_file = {}, False, None
+    frames, last = [], None   # marker lines since the previous instruction (innermost first)
+    for ln in dis:
+        if ln.startswith("//---") and ".text." in ln:
+            inside = kern in ln
+        if not inside:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            frames.append((m.group(1), int(m.group(2))))
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]+)\*/", ln)
+        if m:
+            if frames:
+                mine = [f for f in frames if f[0].endswith(".cu")]
+                if mine:
+                    last = mine[0][1]
+                    src_file = mine[0][0]
+                frames = []
+            if last is not None:
+                addr2line[int(m.group(1), 16)] = last
+    rows = list(csv.reader(open(sass_csv)))
+    # find the block of the requested kernel
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and ("1>" in r[1] if "Lb1" in kern else "0>" in r[1]))
+    hdr = rows[start + 1]
+    ci = {h: i for i, h in enumerate(hdr)}
+    base = None
+    per_line = defaultdict(lambda: [0, 0, 0])
+    total = [0, 0, 0]
+    for r in rows[start + 2:]:
+        if not r or r[0] == "Kernel Name":
+            break
+        a = int(r[ci["Address"]], 16) if r[ci["Address"]].startswith("0x") else int(r[ci["Address"]])
+        if base is None:
+            base = a
+        line = addr2line.get(a - base, -1)
+        ex = int(r[ci["Instructions Executed"]] or 0)
+        th = int(r[ci["Thread Instructions Executed"]] or 0)
+        sm = int(r[ci["# Samples"]] or 0)
+        for acc in (per_line[line], total):
+            acc[0] += ex; acc[1] += th; acc[2] += sm
+    src = open(src_file).read().splitlines() if src_file else []
+    # function ranges: crude scan for "__device__ ... name(" / "__global__"
+    funcs = []
+    for i, l in enumerate(src, 1):
+        m = re.match(r"\s*(?:template <[^>]*>\s*)?(?:__device__|__global__)[^;]*?\b(\w+)\s*\(", l)
+        if m and not l.strip().endswith(";"):
+            funcs.append((i, m.group(1)))
+    def func_of(line):
+        name = "?"
+        for i, n in funcs:
+            if i <= line:
+                name = n
+        return name
+    per_func = defaultdict(lambda: [0, 0, 0])
+    for line, v in per_line.items():
+        f = func_of(line)
+        for k in range(3):
+            per_func[f][k] += v[k]
+    print(f"total warp-instr {total[0]:,}  avg active threads {total[1] / max(total[0], 1):.1f}  samples {total[2]:,}")
+    print("--- per function (warp-instr %, samples %, avg threads)")
+    for f, v in sorted(per_func.items(), key=lambda kv: -kv[1][2]):
+        print(f"{f:22s} instr {100 * v[0] / total[0]:5.1f}%  samples {100 * v[2] / max(total[2], 1):5.1f}%  thr {v[1] / max(v[0], 1):4.1f}")
+    print(f"--- top {top} lines by stall samples")
+    for line, v in sorted(per_line.items(), key=lambda kv: -kv[1][2])[:top]:
+        text = src[line - 1].strip()[:110] if 0 < line <= len(src) else ""
+        print(f"{line:5d} instr {100 * v[0] / total[0]:5.2f}% samples {100 * v[2] / max(total[2], 1):5.2f}% thr {v[1] / max(v[0], 1):4.1f} | {text}")
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -410,9 +411,8 @@ __device__ void passive_actuation(const Warp& w, const float bias[kNvSlots], flo
   }
 }
 
-// smooth.crb + support.make_m into the sparse rows of L1, then the damping-augmented copy L2, then both
-// L^T D L factorisations in one sweep (smooth.factor_m, and the one forward.euler would do later)
-__device__ void crb_factor(const Warp& w) {
+// smooth.crb + support.make_m into the sparse rows of L1 (raw M), plus the damping-augmented copy in L2
+__device__ void build_m(const Warp& w) {
   const DevModel& m = w.m;
   float* crb = w.at(m.o_cin);
   const float* cdof = w.at(m.o_cdof);
@@ -450,67 +450,93 @@ __device__ void crb_factor(const Warp& w) {
     L2[e] = (i == m.m_col[e]) ? L1[e] + m.dt * m.dof_damping[i] : L1[e];
   }
   __syncwarp();
-  float* sD = w.at(m.o_cin + m.c_sD);
-  for (int k = m.nv - 1; k >= 0; --k) {
-    const int adr = m.dof_madr[k], c = m.dof_depth[k];
-    const float d1 = L1[adr], d2 = L2[adr];
-    const float inv1 = 1.f / d1, inv2 = 1.f / d2;
-    const int npair = c * (c + 1) / 2;
-    for (int p = w.lane; p < npair; p += 32) {
-      const int a = m.tri_a[p] + 1, b = m.tri_b[p] + 1;
-      const int tgt = m.dof_madr[m.m_anc[adr + a]] + (b - a);
-      L1[tgt] -= L1[adr + a] * L1[adr + b] * inv1;
-      L2[tgt] -= L2[adr + a] * L2[adr + b] * inv2;
-    }
-    __syncwarp();
-    for (int a = 1 + w.lane; a <= c; a += 32) { L1[adr + a] *= inv1; L2[adr + a] *= inv2; }
-    if (w.lane == 0) { L1[adr] = inv1; L2[adr] = inv2; sD[k] = d1; }
-    __syncwarp();
-  }
 }
 
-// x <- (L^T D L)^-1 x in shared memory; scatter form (mj_solveLD order), no shuffles
-__device__ void solve_ld(const Warp& w, const float* L, float* x) {
+// out = M x with the RAW sparse symmetric M in L1 (called before the factorisation overwrites it); x in shared memory
+__device__ void mul_m_raw(const Warp& w, const float* x, float out[kNvSlots]) {
   const DevModel& m = w.m;
-  for (int i = m.nv - 1; i >= 0; --i) {
-    const int adr = m.dof_madr[i], c = m.dof_depth[i];
-    const float xi = x[i];
-    for (int a = 1 + w.lane; a <= c; a += 32) x[m.m_anc[adr + a]] -= L[adr + a] * xi;
-    __syncwarp();
-  }
-  for (int d = w.lane; d < m.nv; d += 32) x[d] *= L[m.dof_madr[d]];
-  __syncwarp();
-  for (int j = 0; j < m.nv; ++j) {
-    const float xj = x[j];
-    for (int t = m.desc_start[j] + w.lane; t < m.desc_start[j + 1]; t += 32) x[m.desc_dof[t]] -= L[m.desc_off[t]] * xj;
-    __syncwarp();
-  }
-}
-
-// out = M x with M = L1^T D L1; x in shared memory (sx), uses sy as scratch
-__device__ void mul_m(const Warp& w, const float* x, float out[kNvSlots]) {
-  const DevModel& m = w.m;
-  const float* L = w.at(m.o_big);
-  const float* sD = w.at(m.o_cin + m.c_sD);
-  float* y = w.at(m.o_cin + m.c_sy);
-  for (int d = w.lane; d < m.nv; d += 32) {
-    const int adr = m.dof_madr[d], c = m.dof_depth[d];
-    float acc = x[d];
-    for (int a = 1; a <= c; ++a) acc += L[adr + a] * x[m.m_anc[adr + a]];
-    y[d] = acc * sD[d];
-  }
-  __syncwarp();
+  const float* M = w.at(m.o_big);
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) {
     const int d = w.lane + 32 * q;
     float acc = 0.f;
     if (d < m.nv) {
-      acc = y[d];
-      for (int t = m.desc_start[d]; t < m.desc_start[d + 1]; ++t) acc += L[m.desc_off[t]] * y[m.desc_dof[t]];
+      const int adr = m.dof_madr[d], c = m.dof_depth[d];
+      for (int a = 0; a <= c; ++a) acc += M[adr + a] * x[m.m_anc[adr + a]];
+      for (int t = m.desc_start[d]; t < m.desc_start[d + 1]; ++t) acc += M[m.desc_off[t]] * x[m.desc_dof[t]];
     }
     out[q] = acc;
   }
-  __syncwarp();
+}
+
+// both L^T D L factorisations (smooth.factor_m of M, and of M + dt*diag(damping) for forward.euler) in one sweep;
+// the pair updates of step k come from a precomputed table (a | b << 8 | target << 16); diagonals end up inverted
+__device__ void factor_dual(const Warp& w) {
+  const DevModel& m = w.m;
+  float* L1 = w.at(m.o_big);
+  float* L2 = w.at(m.o_big + m.nMpad);
+  for (int k = m.nv - 1; k >= 0; --k) {
+    const int c = m.u_depth[k], adr = int(m.u_rowend[k]) - c;
+    const float inv1 = 1.f / L1[adr], inv2 = 1.f / L2[adr];
+    const int pe = m.pair_start[k + 1];
+    for (int p = m.pair_start[k] + w.lane; p < pe; p += 32) {
+      const uint32_t e = m.pair_tab[p];
+      const int a = adr + int(e & 0xffu), b = adr + int((e >> 8) & 0xffu), tgt = int(e >> 16);
+      L1[tgt] -= L1[a] * L1[b] * inv1;
+      L2[tgt] -= L2[a] * L2[b] * inv2;
+    }
+    __syncwarp();
+    for (int a = 1 + w.lane; a <= c; a += 32) { L1[adr + a] *= inv1; L2[adr + a] *= inv2; }
+    if (w.lane == 0) { L1[adr] = inv1; L2[adr] = inv2; }
+    __syncwarp();
+  }
+}
+
+// x <- (L^T D L)^-1 x with x in REGISTERS (lane l owns dofs l + 32 t): mj_solveLD order, the pivot value travels by
+// warp shuffle, ancestor / descendant tests are bit masks, L is read from shared memory; no barriers
+template <int S>
+__device__ __forceinline__ void solve_up(const DevModel& m, const float* L, float (&x)[kNvSlots], const uint32_t (&dm)[kNvSlots][kNvSlots],
+                                         const int (&dep)[kNvSlots]) {
+  const int hi = min(31, m.nv - 1 - 32 * S);
+  for (int li = hi; li >= 0; --li) {
+    const float xi = __shfl_sync(FULLMASK, x[S], li);
+    const int re = m.u_rowend[li + 32 * S];
+#pragma unroll
+    for (int t = 0; t <= S; ++t)
+      if (m.slot_used[t][S] && ((dm[t][S] >> li) & 1u)) x[t] -= L[re - dep[t]] * xi;
+  }
+}
+template <int S>
+__device__ __forceinline__ void solve_down(const DevModel& m, const float* L, float (&x)[kNvSlots], const uint32_t (&am)[kNvSlots][kNvSlots],
+                                           const int (&rend)[kNvSlots]) {
+  const int hi = min(31, m.nv - 1 - 32 * S);
+  for (int lj = 0; lj <= hi; ++lj) {
+    const float xj = __shfl_sync(FULLMASK, x[S], lj);
+    const int dj = m.u_depth[lj + 32 * S];
+#pragma unroll
+    for (int t = S; t < kNvSlots; ++t)
+      if (m.slot_used[S][t] && ((am[t][S] >> lj) & 1u)) x[t] -= L[rend[t] - dj] * xj;
+  }
+}
+__device__ __noinline__ void solve_reg(const DevModel& m, const float* L, float (&x)[kNvSlots], int lane) {
+  uint32_t dm[kNvSlots][kNvSlots], am[kNvSlots][kNvSlots];
+  int dep[kNvSlots], rend[kNvSlots];
+#pragma unroll
+  for (int t = 0; t < kNvSlots; ++t) {
+    dep[t] = m.depth_me[t * 32 + lane];
+    rend[t] = m.rowend_me[t * 32 + lane];
+#pragma unroll
+    for (int s2 = 0; s2 < kNvSlots; ++s2) { dm[t][s2] = m.dmask[(t * 3 + s2) * 32 + lane]; am[t][s2] = m.amask[(t * 3 + s2) * 32 + lane]; }
+  }
+  solve_up<2>(m, L, x, dm, dep);
+  solve_up<1>(m, L, x, dm, dep);
+  solve_up<0>(m, L, x, dm, dep);
+#pragma unroll
+  for (int t = 0; t < kNvSlots; ++t)
+    if (lane + 32 * t < m.nv) x[t] *= L[rend[t] - dep[t]];
+  solve_down<0>(m, L, x, am, rend);
+  solve_down<1>(m, L, x, am, rend);
+  solve_down<2>(m, L, x, am, rend);
 }
 
 // ---------------------------------------------------------------------------------------------- constraints
@@ -739,7 +765,8 @@ __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float J
 
 struct SolverOut { float qacc[kNvSlots], qfc[kNvSlots], force[kRowSlots]; };
 
-__device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots], const float qas[kNvSlots], SolverOut& so) {
+__device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots], const float qas[kNvSlots],
+                         const float Maw[kNvSlots], SolverOut& so) {
   const DevModel& m = w.m;
   float* sx = w.at(m.o_cin + m.c_sx);
   const float* L1 = w.at(m.o_big);
@@ -747,9 +774,8 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   vget(w, w.at(m.o_warm), warm);
 
   // ---- warm-start choice: cost(qacc_warmstart) vs cost(qacc_smooth)
-  float Jw[kRowSlots], Js[kRowSlots], Maw[kNvSlots];
+  float Jw[kRowSlots], Js[kRowSlots];
   apply_J(w, r, w.at(m.o_warm), Jw);
-  mul_m(w, w.at(m.o_warm), Maw);
   vput(w, sx, qas);
   __syncwarp();
   apply_J(w, r, sx, Js);
@@ -773,7 +799,8 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
 #pragma unroll
   for (int k = 0; k < kRowSlots; ++k) Jaref[k] = use_warm ? Jw[k] : Js[k];
 
-  float force[kRowSlots], qfc[kNvSlots], grad[kNvSlots], Mgrad[kNvSlots], search[kNvSlots];
+  // mv = M search is carried by recurrence: search = -M^-1 grad + beta search  =>  M search = -grad + beta (M search_prev)
+  float force[kRowSlots], qfc[kNvSlots], grad[kNvSlots], Mgrad[kNvSlots], search[kNvSlots], mv[kNvSlots];
   float gauss, cost = use_warm ? cw : cs, prev_cost = __int_as_float(0x7f800000);
   auto update_constraint = [&](bool with_cost) {
     float c = 0.f;
@@ -793,11 +820,9 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   auto update_gradient = [&]() {
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) grad[q] = Ma[q] - qfs[q] - qfc[q];
-    vput(w, sx, grad);
-    __syncwarp();
-    solve_ld(w, L1, sx);
-    vget(w, sx, Mgrad);
-    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) Mgrad[q] = grad[q];
+    solve_reg(m, L1, Mgrad, w.lane);
   };
   // Context.create: cost = inf -> update_constraint sets prev_cost = inf, cost = c
   {
@@ -805,7 +830,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     update_constraint(true);
     update_gradient();
 #pragma unroll
-    for (int q = 0; q < kNvSlots; ++q) search[q] = -Mgrad[q];
+    for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q]; mv[q] = -grad[q]; }
   }
   const float scale = m.meaninertia_scale;
   for (int iter = 0;; ++iter) {
@@ -819,10 +844,9 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     // ---- _linesearch
     const float smag = sqrtf(vdot(search, search)) * scale;
     const float gtol = m.tolerance * m.ls_tolerance * smag;
-    float mv[kNvSlots], jv[kRowSlots];
+    float jv[kRowSlots];
     vput(w, sx, search);
     __syncwarp();
-    mul_m(w, sx, mv);
     apply_J(w, r, sx, jv);
     float qg[3];
     {
@@ -892,7 +916,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     float beta = wsum(num) / fmaxf(kMinVal, wsum(den));
     beta = fmaxf(0.f, beta);
 #pragma unroll
-    for (int q = 0; q < kNvSlots; ++q) search[q] = -Mgrad[q] + beta * search[q];
+    for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q] + beta * search[q]; mv[q] = -grad[q] + beta * mv[q]; }
   }
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) { so.qacc[q] = qacc[q]; so.qfc[q] = qfc[q]; }
@@ -913,16 +937,17 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   com_vel_rne(w, fo.bias);
   passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
   __syncwarp();
-  crb_factor(w);
-  float* sx = w.at(m.o_cin + m.c_sx);
-  vput(w, sx, fo.qfs);
+  build_m(w);
+  float Maw[kNvSlots];
+  mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  solve_ld(w, w.at(m.o_big), sx);
-  vget(w, sx, fo.qas);
-  __syncwarp();
+  factor_dual(w);
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
+  solve_reg(m, w.at(m.o_big), fo.qas, w.lane);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
-  solve_cg(w, r, fo.qfs, fo.qas, fo.so);
+  solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
   vput(w, w.at(m.o_warm), fo.so.qacc);
   __syncwarp();
 }
@@ -930,14 +955,10 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
 // forward.euler + _advance
 __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   const DevModel& m = w.m;
-  float* sx = w.at(m.o_cin + m.c_sx);
-  float rhs[kNvSlots], qacc[kNvSlots];
+  float qacc[kNvSlots];
 #pragma unroll
-  for (int q = 0; q < kNvSlots; ++q) rhs[q] = fo.qfs[q] + fo.so.qfc[q];
-  vput(w, sx, rhs);
-  __syncwarp();
-  solve_ld(w, w.at(m.o_big + m.nMpad), sx);
-  vget(w, sx, qacc);
+  for (int q = 0; q < kNvSlots; ++q) qacc[q] = fo.qfs[q] + fo.so.qfc[q];
+  solve_reg(m, w.at(m.o_big + m.nMpad), qacc, w.lane);
   float* qpos = w.at(m.o_qpos);
   float* qvel = w.at(m.o_qvel);
   float* act = w.at(m.o_act);
@@ -976,6 +997,8 @@ __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
 }
 
 // ---------------------------------------------------------------------------------------------- task layer
+// jnp.minimum propagates NaN (fminf returns the non-NaN operand)
+__device__ __forceinline__ float jminf(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
 __device__ __forceinline__ float nan_to_num(float x) {
   if (isnan(x)) return 0.f;
   if (isinf(x)) return x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
@@ -1158,7 +1181,7 @@ __global__ void __launch_bounds__(128) tmjx_env_kernel(const __grid_constant__ K
         for (int k = 0; k < 4; ++k) { qs[k] = qs[k] / ns; qt[k] = qt[k] / nt; }
       }
       const float qd = qs[0] * qt[0] + qs[1] * qt[1] + qs[2] * qt[2] + qs[3] * qt[3];
-      const float bq = 0.5f * acosf(fminf(1.f, 2.f * qd * qd - 1.f));
+      const float bq = 0.5f * acosf(jminf(1.f, 2.f * qd * qd - 1.f));
       const float quat_distance = bq * bq;
       const float quat_reward = cfg.quat_reward_weight * expf(-cfg.quat_reward_exp_scale * quat_distance);
       float jd = 0.f;
@@ -1186,7 +1209,7 @@ __global__ void __launch_bounds__(128) tmjx_env_kernel(const __grid_constant__ K
       float en = 0.f;
 #pragma unroll
       for (int q = 0; q < kNvSlots; ++q) { const int d = lane + 32 * q; if (d >= 6 && d < m.nv) en += fabsf(qvel[d]) * fabsf(fo.qfa[q]); }
-      const float energy_cost = cfg.energy_cost_weight * fminf(wsum(en), 50.f);
+      const float energy_cost = cfg.energy_cost_weight * jminf(wsum(en), 50.f);
       const float torso_z = xpos[cfg.torso_idx * 3 + 2];
       float healthy = torso_z < cfg.healthy_z_min ? 0.f : 1.f;
       if (torso_z > cfg.healthy_z_max) healthy = 0.f;
@@ -1390,6 +1413,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
   m->envs_per_block = 4;
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) m->envs_per_block = std::max(1, std::min(4, atoi(e)));  // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));

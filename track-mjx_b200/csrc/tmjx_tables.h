@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -51,6 +52,18 @@ struct DevModel {
   const float *dof_armature, *dof_damping;
   // ---- sparse inertia structure
   const uint8_t *m_anc /* [nM] dof id at (row, position) */, *m_row, *m_col /* entry -> (i, j) */, *tri_a, *tri_b;
+  /* register-resident triangular solves: lane l owns dofs l + 32 t.  dmask[(t*3+s)*32 + l] = bit li set when dof
+   * li + 32 s is a DESCENDANT of dof l + 32 t; amask likewise for ANCESTORS; rowend_me[t*32+l] = madr + depth of
+   * the lane's dof (index of L[i][j] is rowend(i) - depth(j)); depth_me its depth.  rowend / depth per dof id are
+   * also kept in the kernel-parameter (constant) bank for uniform access. */
+  const uint32_t *dmask, *amask;
+  const int *rowend_me, *depth_me;
+  uint16_t u_rowend[96];
+  uint8_t u_depth[96];
+  uint8_t slot_used[3][3];    /* [t][s]: some lane has a non-zero dmask word (same as amask[s][t]) */
+  /* factorisation pair table: for step k the entries [pair_start[k], pair_start[k+1]) = a | b << 8 | target << 16 */
+  const uint32_t* pair_tab;
+  const int* pair_start;
   const int* desc_start;      /* [nv+1] */
   const uint8_t* desc_dof;    /* descendant dof id */
   const uint16_t* desc_off;   /* offset of L[desc][j] in the sparse array */
@@ -202,6 +215,35 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   }
   desc_start[nv] = int(desc_dof.size());
 
+  // ---- tables for the shuffle-based solves and the factorisation
+  std::vector<int32_t> dmask(9 * 32, 0), amask(9 * 32, 0), rowend_me(3 * 32, 0), depth_me(3 * 32, 0);
+  std::memset(m.u_rowend, 0, sizeof(m.u_rowend));
+  std::memset(m.u_depth, 0, sizeof(m.u_depth));
+  std::memset(m.slot_used, 0, sizeof(m.slot_used));
+  for (int i = 0; i < nv; ++i) {
+    m.u_rowend[i] = uint16_t(dof_madr[i] + dof_depth[i]);
+    m.u_depth[i] = uint8_t(dof_depth[i]);
+    rowend_me[(i / 32) * 32 + (i % 32)] = dof_madr[i] + dof_depth[i];
+    depth_me[(i / 32) * 32 + (i % 32)] = dof_depth[i];
+    for (int a = 1; a <= dof_depth[i]; ++a) {
+      const int j = m_anc[dof_madr[i] + a];  // j is an ancestor of i
+      dmask[((j / 32) * 3 + (i / 32)) * 32 + (j % 32)] |= int32_t(1u << (i % 32));
+      amask[((i / 32) * 3 + (j / 32)) * 32 + (i % 32)] |= int32_t(1u << (j % 32));
+      m.slot_used[j / 32][i / 32] = 1;
+    }
+  }
+  std::vector<int32_t> pair_tab, pair_start(nv + 1, 0);
+  for (int k = 0; k < nv; ++k) {
+    pair_start[k] = int(pair_tab.size());
+    const int c = dof_depth[k];
+    for (int bb = 1; bb <= c; ++bb)
+      for (int a = 1; a <= bb; ++a) {
+        const int tgt = dof_madr[m_anc[dof_madr[k] + a]] + (bb - a);
+        pair_tab.push_back(int32_t(uint32_t(a) | (uint32_t(bb) << 8) | (uint32_t(tgt) << 16)));
+      }
+  }
+  pair_start[nv] = int(pair_tab.size());
+
   // ---- per dof helpers
   std::vector<int32_t> dof_qadr(nv, -1), dof_limit(nv, -1);
   for (int j = 0; j < njnt; ++j) if (jnt_type[j] == kJntHinge) dof_qadr[jnt_dofadr[j]] = jnt_qposadr[j];
@@ -341,6 +383,9 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   PI(dof_qadr, dof_qadr);
   PF(dof_armature, b.f32("dof_armature")); PF(dof_damping, b.f32("dof_damping"));
   P8(m_anc, m_anc); P8(m_row, m_row); P8(m_col, m_col); P8(tri_a, tri_a); P8(tri_b, tri_b);
+  m.dmask = TMJX_OFF(uint32_t, push(t.i32, dmask)); m.amask = TMJX_OFF(uint32_t, push(t.i32, amask));
+  PI(rowend_me, rowend_me); PI(depth_me, depth_me);
+  m.pair_tab = TMJX_OFF(uint32_t, push(t.i32, pair_tab)); PI(pair_start, pair_start);
   PI(desc_start, desc_start); P8(desc_dof, desc_dof);
   m.desc_off = TMJX_OFF(uint16_t, push(t.u16, desc_off));
   PF(act_gain, act_gain); PF(act_ctrl_lo, a_lo); PF(act_ctrl_hi, a_hi); PF(act_dyn_inv, a_dyninv); PF(act_bias, act_biasprm);
@@ -397,6 +442,10 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   RI(dof_body); RI(dof_jnt); RI(dof_madr); RI(dof_depth); RI(dof_limit); RI(dof_qadr);
   RF(dof_armature); RF(dof_damping);
   R8(m_anc); R8(m_row); R8(m_col); R8(tri_a); R8(tri_b);
+  m.dmask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dmask);
+  m.amask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.amask);
+  m.pair_tab = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.pair_tab);
+  RI(rowend_me); RI(depth_me); RI(pair_start);
   RI(desc_start); R8(desc_dof);
   m.desc_off = d16 + reinterpret_cast<uintptr_t>(m.desc_off);
   RF(act_gain); RF(act_ctrl_lo); RF(act_ctrl_hi); RF(act_dyn_inv); RF(act_bias); RF(act_force_lo); RF(act_force_hi);
