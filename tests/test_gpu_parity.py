@@ -121,23 +121,32 @@ def test_control_step_parity_and_drift(walker, clips2):
 
 
 def test_done_flags_and_frames_bit_exact_many_envs(walker, clips2):
-    """1024 envs, mixed regimes (some terminating): flags, frame indices and integer state are bit-exact."""
+    """1024 envs, mixed regimes (some terminating): flags, frame indices and integer state are bit-exact.
+
+    The rollout that produces the inputs is not auto-reset, so a handful of envs have numerically exploded
+    (|qvel| ~ 1e13): there the fp32 and fp64 oracles disagree with EACH OTHER on the flags, i.e. the reference value
+    is undefined at fp32 resolution.  Flags are compared on every env whose state is sane (|qvel| < 1e4) and on which
+    the two oracles agree; that set must be nearly all envs.  `done` and `cur_frame` are compared on all envs."""
     n = 1024
     st = rollout_states(walker, clips2, n, 6, 0.3, seed=4)
     cfg = make_cfg(walker, physics_steps_per_control_step=1)
-    o32 = Oracle(walker.blob, cfg, clips2, dtype=np.float32)
+    o32, o64 = Oracle(walker.blob, cfg, clips2, dtype=np.float32), Oracle(walker.blob, cfg, clips2, dtype=np.float64)
     g = Stepper(walker.blob, cfg, clips2, n, 0)
-    a = o32.alloc(n, debug=False)
-    common.put(a, st); common.put(g.buf, st)
+    a, b = o32.alloc(n, debug=False), o64.alloc(n, debug=False)
+    common.put(a, st); common.put(b, st); common.put(g.buf, st)
     act = (0.3 * np.random.default_rng(9).normal(size=(n, walker.nu))).astype(np.float32)
     o32.step(a, act)
+    o64.step(b, act)
     g.step(torch.from_numpy(act).cuda())
     gb = common.get(g.buf)
     m = config.METRIC_NAMES
+    flags = [m.index(k) for k in ("too_far", "bad_pose", "bad_quat", "fall", "nan", "done")]
+    sane = (np.abs(st["qvel"]).max(1) < 1e4) & (a["metrics"][:, flags] == b["metrics"][:, flags]).all(1)
+    assert sane.sum() >= 0.98 * n
     assert a["done"].sum() > 10 and (a["done"] == 0).sum() > 10          # both outcomes present
     assert (gb["done"] == a["done"]).all()
-    for name in ("too_far", "bad_pose", "bad_quat", "fall", "nan", "done"):
-        assert (gb["metrics"][:, m.index(name)] == a["metrics"][:, m.index(name)]).all(), name
+    for name, i in zip(("too_far", "bad_pose", "bad_quat", "fall", "nan", "done"), flags):
+        assert (gb["metrics"][sane, i] == a["metrics"][sane, i]).all(), name
     assert (gb["cur_frame"] == a["cur_frame"]).all()
     g.close()
 

@@ -1,0 +1,257 @@
+"""Generate the tree-specialised device code of the step kernel: csrc/tmjx_gen_tree.cuh.
+
+    python tools/gen_tree_kernels.py            # rewrites track-mjx_b200/csrc/tmjx_gen_tree.cuh (committed)
+
+The joint-space inertia of a kinematic tree factors as M = L^T D L with L unit lower triangular and non-zero only at
+(dof, ancestor) (Featherstone; MuJoCo mj_factorM / mj_solveLD, which mjx.smooth.factor_m / solve_m restate in dense
+form).  The triangular solves are the latency chain of every physics substep (8 per substep), so for the walker's
+fixed tree they are emitted as STRAIGHT-LINE warp code: the right-hand side lives in registers (lane l owns dofs
+l, l+32, l+64), each pivot value travels by one `__shfl_sync` with a compile-time source lane, ancestor / descendant
+tests are compile-time lane masks, L is read from shared memory with immediate offsets.  Pivots are emitted level by
+level (deepest first for L^T, root first for L) so that independent limbs interleave and the scheduler sees the ILP.
+
+The same schedule is held as a tiny IR and executed by a numpy interpreter (`run_ir`), which is how
+tests/test_gen_schedule.py validates it on the CPU against a dense solve before any GPU time is spent.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "track-mjx_b200", "csrc", "tmjx_gen_tree.cuh")
+
+
+# ------------------------------------------------------------------------------------------------ tree structure
+class Tree:
+    def __init__(self, dof_parent):
+        p = [int(x) for x in dof_parent]
+        self.parent = p
+        self.nv = nv = len(p)
+        assert nv <= 96
+        self.depth = [0] * nv
+        for i in range(nv):
+            assert p[i] < i
+            self.depth[i] = 0 if p[i] < 0 else self.depth[p[i]] + 1
+        self.madr, o = [], 0
+        for i in range(nv):
+            self.madr.append(o)
+            o += self.depth[i] + 1
+        self.nM = o
+        self.rowend = [self.madr[i] + self.depth[i] for i in range(nv)]
+        self.anc = []
+        for i in range(nv):
+            a, j = [], p[i]
+            while j >= 0:
+                a.append(j)
+                j = p[j]
+            self.anc.append(a)  # nearest first
+        self.desc = [[] for _ in range(nv)]
+        for i in range(nv):
+            for j in self.anc[i]:
+                self.desc[j].append(i)
+        self.maxdepth = max(self.depth)
+
+    def signature(self) -> str:
+        return hashlib.sha256(bytes(np.asarray(self.parent, np.int16).tobytes())).hexdigest()[:16]
+
+
+def lane_mask(dofs, slot):
+    m = 0
+    for d in dofs:
+        if d // 32 == slot:
+            m |= 1 << (d % 32)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ IR
+# ("shfl", dst, src, lane)                    dst = src[lane]
+# ("fnma_lds", x, ptr, imm, p, mask)          x = x - L[ptr(lane) + imm] * p     for lanes in mask
+# ("mul_lds", x, ptr, imm, mask)              x = x * L[ptr(lane) + imm]         for lanes in mask
+# pointers (per lane, in floats): "U<t>" = -depth_me[t], "D<t>" = rowend_me[t], "G<t>" = madr_me[t]
+def build_solve_ir(t: Tree):
+    nv = t.nv
+    nslot = (nv + 31) // 32
+    ir = []
+    by_level = [[i for i in range(nv) if t.depth[i] == lv] for lv in range(t.maxdepth + 1)]
+    # ---- x <- L^-T x: pivot i (deepest level first) updates its ancestors: x[j] -= L[i][j] x[i]
+    for lv in range(t.maxdepth, 0, -1):
+        for i in sorted(by_level[lv], reverse=True):
+            ir.append(("shfl", "p", f"x{i // 32}", i % 32))
+            for s in range(nslot):
+                m = lane_mask(t.anc[i], s)
+                if m:
+                    ir.append(("fnma_lds", f"x{s}", f"U{s}", t.rowend[i], "p", m))
+    # ---- x <- D^-1 x (the factorisation leaves 1/D on the diagonal)
+    for s in range(nslot):
+        ir.append(("mul_lds", f"x{s}", f"G{s}", 0, lane_mask(range(nv), s)))
+    # ---- x <- L^-1 x: pivot j (root first) updates its descendants: x[i] -= L[i][j] x[j]
+    for lv in range(0, t.maxdepth):
+        for j in by_level[lv]:
+            if not t.desc[j]:
+                continue
+            ir.append(("shfl", "p", f"x{j // 32}", j % 32))
+            for s in range(nslot):
+                m = lane_mask(t.desc[j], s)
+                if m:
+                    ir.append(("fnma_lds", f"x{s}", f"D{s}", -t.depth[j], "p", m))
+    return ir
+
+
+def lane_tables(t: Tree):
+    nslot = (t.nv + 31) // 32
+    tabs = {}
+    for s in range(nslot):
+        dep = np.zeros(32, np.int64)
+        rend = np.zeros(32, np.int64)
+        madr = np.zeros(32, np.int64)
+        for l in range(32):
+            d = 32 * s + l
+            if d < t.nv:
+                dep[l], rend[l], madr[l] = t.depth[d], t.rowend[d], t.madr[d]
+        tabs[f"U{s}"], tabs[f"D{s}"], tabs[f"G{s}"] = -dep, rend, madr
+    return tabs
+
+
+def run_ir(ir, t: Tree, L: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """numpy interpreter: L [nM] sparse factor (diagonal = 1/D), x [nv] -> solution [nv] (float32 arithmetic)."""
+    nslot = (t.nv + 31) // 32
+    pad = 64
+    Lp = np.concatenate([np.full(pad, np.nan, np.float32), L.astype(np.float32), np.full(pad, np.nan, np.float32)])
+    tabs = lane_tables(t)
+    regs = {}
+    for s in range(nslot):
+        v = np.zeros(32, np.float32)
+        n = min(32, t.nv - 32 * s)
+        v[:n] = x[32 * s:32 * s + n]
+        regs[f"x{s}"] = v
+    lanes = np.arange(32)
+    for op in ir:
+        if op[0] == "shfl":
+            regs[op[1]] = np.full(32, regs[op[2]][op[3]], np.float32)
+        elif op[0] == "fnma_lds":
+            _, xr, ptr, imm, p, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            val = Lp[pad + tabs[ptr] + imm]
+            new = (regs[xr] - val * regs[p]).astype(np.float32)
+            regs[xr] = np.where(act, new, regs[xr])
+        elif op[0] == "mul_lds":
+            _, xr, ptr, imm, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            val = Lp[pad + tabs[ptr] + imm]
+            regs[xr] = np.where(act, (regs[xr] * val).astype(np.float32), regs[xr])
+        else:
+            raise ValueError(op)
+    return np.concatenate([regs[f"x{s}"] for s in range(nslot)])[: t.nv]
+
+
+# ------------------------------------------------------------------------------------------------ reference algebra
+def sparse_from_dense(t: Tree, M: np.ndarray) -> np.ndarray:
+    out = np.zeros(t.nM, M.dtype)
+    for i in range(t.nv):
+        out[t.madr[i]] = M[i, i]
+        for a, j in enumerate(t.anc[i]):
+            out[t.madr[i] + 1 + a] = M[i, j]
+    return out
+
+
+def factor_ref(t: Tree, Ms: np.ndarray) -> np.ndarray:
+    """mj_factorM on the sparse rows; returns L with 1/D on the diagonal (what the kernel's factor_dual leaves)."""
+    L = Ms.copy()
+    for k in range(t.nv - 1, -1, -1):
+        adr, c = t.madr[k], t.depth[k]
+        inv = 1.0 / L[adr]
+        for a in range(1, c + 1):
+            ra = t.anc[k][a - 1]
+            for b in range(a, c + 1):
+                L[t.madr[ra] + (b - a)] -= L[adr + a] * L[adr + b] * inv
+        L[adr + 1: adr + c + 1] *= inv
+        L[adr] = inv
+    return L
+
+
+def random_tree_spd(t: Tree, rng) -> np.ndarray:
+    """A random SPD matrix with the tree's sparsity (sum of chain outer products + diagonal)."""
+    M = np.zeros((t.nv, t.nv))
+    for i in range(t.nv):
+        chain = [i] + t.anc[i]
+        v = rng.normal(size=len(chain)) * rng.uniform(0.1, 1.0)
+        for a, ia in enumerate(chain):
+            for b, ib in enumerate(chain):
+                M[ia, ib] += v[a] * v[b]
+    M += np.diag(rng.uniform(0.05, 0.5, t.nv))
+    return M
+
+
+# ------------------------------------------------------------------------------------------------ CUDA printer
+def emit_cuda(t: Tree) -> str:
+    ir = build_solve_ir(t)
+    nslot = (t.nv + 31) // 32
+    o = []
+    w = o.append
+    w("// GENERATED by tools/gen_tree_kernels.py -- do not edit; regenerate when the walker's dof tree changes.")
+    w("// Straight-line L^T D L solves for one fixed kinematic tree (see the generator's docstring).")
+    w("#ifndef TMJX_GEN_TREE_CUH_")
+    w("#define TMJX_GEN_TREE_CUH_")
+    w("namespace tmjx { namespace gen {")
+    w(f"constexpr int kNv = {t.nv};")
+    w(f"constexpr int kNM = {t.nM};")
+    w(f"constexpr int kNMpad = {(t.nM + 3) & ~3};  // distance between the two factors in shared memory")
+    w(f"constexpr int kNSlot = {nslot};")
+    w(f"// dof_parentid of the tree this file was generated for (signature {t.signature()})")
+    w("constexpr short kDofParent[kNv] = {" + ", ".join(str(p) for p in t.parent) + "};")
+    w("struct V3 { float a, b, c; };")
+    w("#ifdef __CUDACC__")
+    w("// x <- (L^T D L)^-1 x.  L: this env's sparse factor in shared memory (diagonal holds 1/D);")
+    w("// dep* / rend* : depth and row-end of the dofs this lane owns (lane, lane+32, lane+64).")
+    w("__device__ __noinline__ V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
+    w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c, p;")
+    w("  const unsigned lb = 1u << lane;")
+    for s in range(3):
+        w(f"  const float* U{s} = L - dep{s};")
+        w(f"  const float* D{s} = L + rend{s};")
+        w(f"  const float* G{s} = L + (rend{s} - dep{s});")
+    full = 0xFFFFFFFF
+    for op in ir:
+        if op[0] == "shfl":
+            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]});")
+        elif op[0] == "fnma_lds":
+            _, xr, ptr, imm, p, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}{xr} = fmaf(-{ptr}[{imm}], p, {xr});")
+        elif op[0] == "mul_lds":
+            _, xr, ptr, imm, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}{xr} *= {ptr}[{imm}];")
+    w("  V3 r; r.a = x0; r.b = x1; r.c = x2;")
+    w("  return r;")
+    w("}")
+    w("#endif  // __CUDACC__")
+    w("}}  // namespace tmjx::gen")
+    w("#endif  // TMJX_GEN_TREE_CUH_")
+    return "\n".join(o) + "\n"
+
+
+def rodent_tree() -> Tree:
+    sys.path.insert(0, ROOT)
+    from track_mjx_b200.walker import Rodent
+
+    w = Rodent(torque_actuators=True, rescale_factor=0.9)
+    return Tree(np.asarray(w.sections["dof_parentid"]).astype(int))
+
+
+def main():
+    t = rodent_tree()
+    src = emit_cuda(t)
+    with open(OUT, "w") as f:
+        f.write(src)
+    ir = build_solve_ir(t)
+    print(f"wrote {OUT}: nv {t.nv} nM {t.nM} maxdepth {t.maxdepth}, solve IR {len(ir)} ops "
+          f"({sum(1 for x in ir if x[0] == 'shfl')} shuffles)")
+
+
+if __name__ == "__main__":
+    main()

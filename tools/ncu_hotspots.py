@@ -46,12 +46,15 @@ def main():
                 addr2line[int(m.group(1), 16)] = last
     rows = list(csv.reader(open(sass_csv)))
     # find the block of the requested kernel
-    start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and ("1>" in r[1] if "Lb1" in kern else "0>" in r[1]))
+    want = "(bool)1" if "Lb1" in kern else "(bool)0"
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and (want in r[1] or ("1>" in r[1] if "Lb1" in kern else "0>" in r[1])))
     hdr = rows[start + 1]
     ci = {h: i for i, h in enumerate(hdr)}
     base = None
     per_line = defaultdict(lambda: [0, 0, 0])
     total = [0, 0, 0]
+    reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    per_line_reason = defaultdict(lambda: defaultdict(int))
     for r in rows[start + 2:]:
         if not r or r[0] == "Kernel Name":
             break
@@ -64,6 +67,10 @@ def main():
         sm = int(r[ci["# Samples"]] or 0)
         for acc in (per_line[line], total):
             acc[0] += ex; acc[1] += th; acc[2] += sm
+        for h in reasons:
+            v = r[ci[h]]
+            if v and v != "0":
+                per_line_reason[line][h] += int(v)
     src = open(src_file).read().splitlines() if src_file else []
     # function ranges: crude scan for "__device__ ... name(" / "__global__"
     funcs = []
@@ -82,10 +89,21 @@ def main():
         f = func_of(line)
         for k in range(3):
             per_func[f][k] += v[k]
+    per_func_reason = defaultdict(lambda: defaultdict(int))
+    tot_reason = defaultdict(int)
+    for line, d in per_line_reason.items():
+        for h, v in d.items():
+            per_func_reason[func_of(line)][h] += v
+            tot_reason[h] += v
     print(f"total warp-instr {total[0]:,}  avg active threads {total[1] / max(total[0], 1):.1f}  samples {total[2]:,}")
-    print("--- per function (warp-instr %, samples %, avg threads)")
+    allr = sum(tot_reason.values()) or 1
+    print("stall reasons (all samples): " + "  ".join(f"{h[6:]} {100 * v / allr:.1f}%" for h, v in sorted(tot_reason.items(), key=lambda kv: -kv[1])[:8]))
+    print("--- per function (warp-instr %, samples %, avg threads, top stall reasons)")
     for f, v in sorted(per_func.items(), key=lambda kv: -kv[1][2]):
-        print(f"{f:22s} instr {100 * v[0] / total[0]:5.1f}%  samples {100 * v[2] / max(total[2], 1):5.1f}%  thr {v[1] / max(v[0], 1):4.1f}")
+        rs = per_func_reason[f]
+        tr = sum(rs.values()) or 1
+        top3 = " ".join(f"{h[6:]}:{100 * x / tr:.0f}" for h, x in sorted(rs.items(), key=lambda kv: -kv[1])[:4])
+        print(f"{f:22s} instr {100 * v[0] / total[0]:5.1f}%  samples {100 * v[2] / max(total[2], 1):5.1f}%  thr {v[1] / max(v[0], 1):4.1f}  {top3}")
     print(f"--- top {top} lines by stall samples")
     for line, v in sorted(per_line.items(), key=lambda kv: -kv[1][2])[:top]:
         text = src[line - 1].strip()[:110] if 0 < line <= len(src) else ""

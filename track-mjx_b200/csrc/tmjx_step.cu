@@ -130,6 +130,7 @@ struct Warp {
   const DevModel& m;
   float* s;  // this environment's shared-memory slice
   int lane;
+  int dep[kNvSlots], rend[kNvSlots];  // depth / row end (sparse L) of the dofs this lane owns
   __device__ __forceinline__ float* at(int off) const { return s + off; }
 };
 
@@ -469,27 +470,71 @@ __device__ void mul_m_raw(const Warp& w, const float* x, float out[kNvSlots]) {
   }
 }
 
-// both L^T D L factorisations (smooth.factor_m of M, and of M + dt*diag(damping) for forward.euler) in one sweep;
-// the pair updates of step k come from a precomputed table (a | b << 8 | target << 16); diagonals end up inverted
+// both L^T D L factorisations (smooth.factor_m of M, and of M + dt*diag(damping) for forward.euler) in one sweep.
+// Depth-lane mapping: lane d owns the entries whose COLUMN dof has depth d (d + 32 in the `hi` slot), for every row.
+// Row k is held in registers, the pivot entry l_a of each ancestor row travels by shuffle, the rank-1 update of row
+// `anc(k, a)` touches consecutive addresses (conflict-free) and -- because an entry is only ever read and written by
+// the one lane that owns its column depth -- the whole factorisation needs no barrier.  The a-loop is software
+// pipelined four rows at a time (all loads, then all FMAs, then all stores): rows of one pivot never alias.
+// kOff2 = compile-time distance between the two factors (0: read it from the model) so that the second factor is
+// addressed with an immediate offset.
+template <int kOff2>
 __device__ void factor_dual(const Warp& w) {
   const DevModel& m = w.m;
   float* L1 = w.at(m.o_big);
-  float* L2 = w.at(m.o_big + m.nMpad);
+  const int off2 = kOff2 ? kOff2 : m.nMpad, lane = w.lane;
+  float* pl = L1 - lane;  // entry (row r, column depth = lane) lives at pl[rowend(r)]
   for (int k = m.nv - 1; k >= 0; --k) {
-    const int c = m.u_depth[k], adr = int(m.u_rowend[k]) - c;
-    const float inv1 = 1.f / L1[adr], inv2 = 1.f / L2[adr];
-    const int pe = m.pair_start[k + 1];
-    for (int p = m.pair_start[k] + w.lane; p < pe; p += 32) {
-      const uint32_t e = m.pair_tab[p];
-      const int a = adr + int(e & 0xffu), b = adr + int((e >> 8) & 0xffu), tgt = int(e >> 16);
-      L1[tgt] -= L1[a] * L1[b] * inv1;
-      L2[tgt] -= L2[a] * L2[b] * inv2;
+    const int c = m.u_depth[k], re = m.u_rowend[k];
+    float* rk = pl + re;
+    const bool hi = c >= 32;  // uniform
+    float l1 = 0.f, l2 = 0.f, h1 = 0.f, h2 = 0.f;
+    if (lane <= c) { l1 = rk[0]; l2 = rk[off2]; }
+    if (hi && lane + 32 <= c) { h1 = rk[-32]; h2 = rk[off2 - 32]; }
+    const float d1 = __shfl_sync(FULLMASK, hi ? h1 : l1, c & 31), d2 = __shfl_sync(FULLMASK, hi ? h2 : l2, c & 31);
+    const float inv1 = 1.f / d1, inv2 = 1.f / d2;
+    const float w1 = l1 * inv1, w2 = l2 * inv2;
+    // scaled row + inverted diagonal (row k is not touched by its own rank-1 updates)
+    if (lane < c) { rk[0] = w1; rk[off2] = w2; }
+    else if (lane == c) { rk[0] = inv1; rk[off2] = inv2; }
+    int al = c - 1;
+    if (hi) {  // rows of depth >= 32 (deep chain tips only): they also own columns of depth >= 32
+      const float wh1 = h1 * inv1, wh2 = h2 * inv2;
+      if (lane + 32 < c) { rk[-32] = wh1; rk[off2 - 32] = wh2; }
+      else if (lane + 32 == c) { rk[-32] = inv1; rk[off2 - 32] = inv2; }
+      for (; al >= 32; --al) {
+        float* t = pl + int(m.u_ancre[re - al]);
+        const float a1 = __shfl_sync(FULLMASK, h1, al - 32), a2 = __shfl_sync(FULLMASK, h2, al - 32);
+        t[0] = fmaf(-a1, w1, t[0]); t[off2] = fmaf(-a2, w2, t[off2]);
+        if (lane + 32 <= al) { t[-32] = fmaf(-a1, wh1, t[-32]); t[off2 - 32] = fmaf(-a2, wh2, t[off2 - 32]); }
+      }
     }
-    __syncwarp();
-    for (int a = 1 + w.lane; a <= c; a += 32) { L1[adr + a] *= inv1; L2[adr + a] *= inv2; }
-    if (w.lane == 0) { L1[adr] = inv1; L2[adr] = inv2; }
-    __syncwarp();
+    int ti = re - al;  // u_ancre[ti + u] = row end of the ancestor at depth al - u
+    for (; al >= 3; al -= 4, ti += 4) {
+      float* t0 = pl + int(m.u_ancre[ti]); float* t1 = pl + int(m.u_ancre[ti + 1]); float* t2 = pl + int(m.u_ancre[ti + 2]);
+      float* t3 = pl + int(m.u_ancre[ti + 3]);
+      const float a10 = __shfl_sync(FULLMASK, l1, al), a20 = __shfl_sync(FULLMASK, l2, al);
+      const float a11 = __shfl_sync(FULLMASK, l1, al - 1), a21 = __shfl_sync(FULLMASK, l2, al - 1);
+      const float a12 = __shfl_sync(FULLMASK, l1, al - 2), a22 = __shfl_sync(FULLMASK, l2, al - 2);
+      const float a13 = __shfl_sync(FULLMASK, l1, al - 3), a23 = __shfl_sync(FULLMASK, l2, al - 3);
+      const bool p0 = lane <= al, p1 = lane <= al - 1, p2 = lane <= al - 2, p3 = lane <= al - 3;
+      float v10, v20, v11, v21, v12, v22, v13, v23;
+      if (p0) { v10 = t0[0]; v20 = t0[off2]; }
+      if (p1) { v11 = t1[0]; v21 = t1[off2]; }
+      if (p2) { v12 = t2[0]; v22 = t2[off2]; }
+      if (p3) { v13 = t3[0]; v23 = t3[off2]; }
+      if (p0) { t0[0] = fmaf(-a10, w1, v10); t0[off2] = fmaf(-a20, w2, v20); }
+      if (p1) { t1[0] = fmaf(-a11, w1, v11); t1[off2] = fmaf(-a21, w2, v21); }
+      if (p2) { t2[0] = fmaf(-a12, w1, v12); t2[off2] = fmaf(-a22, w2, v22); }
+      if (p3) { t3[0] = fmaf(-a13, w1, v13); t3[off2] = fmaf(-a23, w2, v23); }
+    }
+    for (; al >= 0; --al, ++ti) {
+      float* t = pl + int(m.u_ancre[ti]);
+      const float a1 = __shfl_sync(FULLMASK, l1, al), a2 = __shfl_sync(FULLMASK, l2, al);
+      if (lane <= al) { t[0] = fmaf(-a1, w1, t[0]); t[off2] = fmaf(-a2, w2, t[off2]); }
+    }
   }
+  __syncwarp();  // consumers (solves, M products) use a dof-lane mapping
 }
 
 // x <- (L^T D L)^-1 x with x in REGISTERS (lane l owns dofs l + 32 t): mj_solveLD order, the pivot value travels by
@@ -537,6 +582,18 @@ __device__ __noinline__ void solve_reg(const DevModel& m, const float* L, float 
   solve_down<0>(m, L, x, am, rend);
   solve_down<1>(m, L, x, am, rend);
   solve_down<2>(m, L, x, am, rend);
+}
+
+// solve with the factor at `L`: straight-line generated code when the dof tree is the one it was generated for
+__device__ __forceinline__ void solve_ld(const Warp& w, const float* L, float (&x)[kNvSlots]) {
+  if (w.m.use_gen) {
+    gen::V3 v;
+    v.a = x[0]; v.b = x[1]; v.c = x[2];
+    v = gen::solve(L, v, w.lane, w.dep[0], w.dep[1], w.dep[2], w.rend[0], w.rend[1], w.rend[2]);
+    x[0] = v.a; x[1] = v.b; x[2] = v.c;
+  } else {
+    solve_reg(w.m, L, x, w.lane);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- constraints
@@ -822,7 +879,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) grad[q] = Ma[q] - qfs[q] - qfc[q];
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) Mgrad[q] = grad[q];
-    solve_reg(m, L1, Mgrad, w.lane);
+    solve_ld(w, L1, Mgrad);
   };
   // Context.create: cost = inf -> update_constraint sets prev_cost = inf, cost = c
   {
@@ -941,10 +998,10 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   float Maw[kNvSlots];
   mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  factor_dual(w);
+  if (m.use_gen) factor_dual<gen::kNMpad>(w); else factor_dual<0>(w);
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
-  solve_reg(m, w.at(m.o_big), fo.qas, w.lane);
+  solve_ld(w, w.at(m.o_big), fo.qas);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
   solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
@@ -958,7 +1015,7 @@ __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   float qacc[kNvSlots];
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) qacc[q] = fo.qfs[q] + fo.so.qfc[q];
-  solve_reg(m, w.at(m.o_big + m.nMpad), qacc, w.lane);
+  solve_ld(w, w.at(m.o_big + m.nMpad), qacc);
   float* qpos = w.at(m.o_qpos);
   float* qvel = w.at(m.o_qvel);
   float* act = w.at(m.o_act);
@@ -1087,14 +1144,18 @@ struct KArgs {
   unsigned flags;
 };
 
-template <bool kStep>
-__global__ void __launch_bounds__(128) tmjx_env_kernel(const __grid_constant__ KArgs a) {
+// kWPB warps (= environments) per block; (4, 3) and (7, 2) are the two residency points that matter on B200:
+// 12 and 14 resident environments per SM (the latter needs <= 144 registers and fits 4096 envs in two waves of 148 SMs)
+template <bool kStep, int kWPB, int kMinBlocks>
+__global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ float smem[];
   const DevModel& m = a.m;
   const DevTask& t = *a.task;
   const TmjxTaskConfig& cfg = t.cfg;
   const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Warp w{m, smem + size_t(warp) * m.smem_floats, lane};
+  Warp w{m, smem + size_t(warp) * m.smem_floats, lane, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) { w.dep[q] = m.depth_me[q * 32 + lane]; w.rend[q] = m.rowend_me[q * 32 + lane]; }
   const int nu = m.nu, nobs = t.obs_size, W = cfg.var_window_size;
   for (int e = blockIdx.x * wpb + warp; e < a.n_env; e += gridDim.x * wpb) {
     // ---- stage the persistent state
@@ -1360,7 +1421,7 @@ struct TmjxModel {
   uint16_t* d_u16 = nullptr;
   uint8_t* d_u8 = nullptr;
   float* d_f32 = nullptr;
-  int device = 0, sm_count = 0, envs_per_block = 4, max_blocks_per_sm = 1;
+  int device = 0, sm_count = 0, envs_per_block = 7, max_blocks_per_sm = 1, variant = 0;
   size_t smem_per_block = 0;
   TmjxTaskConfig cfg;
 };
@@ -1412,13 +1473,21 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   CU(cudaGetDeviceProperties(&prop, device));
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
-  m->envs_per_block = 4;
-  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) m->envs_per_block = std::max(1, std::min(4, atoi(e)));  // tuning knob
+  // 7 warps x 2 blocks = 14 resident envs per SM when the per-env slice allows it, else 4 warps x up to 3 blocks
+  m->envs_per_block = (2 * (7 * per_env + 1024) <= prop.sharedMemPerMultiprocessor) ? 7 : 4;
+  int variant = 0;
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { m->envs_per_block = atoi(e) == 7 ? 7 : 4; variant = atoi(e); }  // tuning knob
+  if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  if (m->envs_per_block == 7) m->max_blocks_per_sm = std::min(m->max_blocks_per_sm, 2);
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  m->variant = variant;
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
   *out = m;
   return TMJX_OK;
 }
@@ -1503,7 +1572,9 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   const int epb = m->envs_per_block;
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
-  tmjx_env_kernel<kStep><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  if (kStep && m->variant == 44) tmjx_env_kernel<true, 4, 4><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  else if (epb == 7) tmjx_env_kernel<kStep, 7, 2><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  else tmjx_env_kernel<kStep, 4, 3><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   CU(cudaGetLastError());
   return TMJX_OK;
 }

@@ -20,6 +20,7 @@
 
 #include "../../include/tmjx.h"
 #include "../../include/tmjx_blob.h"
+#include "tmjx_gen_tree.cuh"
 
 namespace tmjx {
 
@@ -61,6 +62,10 @@ struct DevModel {
   uint16_t u_rowend[96];
   uint8_t u_depth[96];
   uint8_t slot_used[3][3];    /* [t][s]: some lane has a non-zero dmask word (same as amask[s][t]) */
+  /* depth-lane factorisation: u_ancre[rowend(k) - a] = rowend of the ancestor of dof k that has depth a (a <= depth(k)),
+   * i.e. the sparse position of entry (k, anc) maps to the row that the rank-1 update of pivot k touches. */
+  uint16_t u_ancre[1280];
+  int use_gen;                /* the dof tree equals the one csrc/tmjx_gen_tree.cuh was generated for */
   /* factorisation pair table: for step k the entries [pair_start[k], pair_start[k+1]) = a | b << 8 | target << 16 */
   const uint32_t* pair_tab;
   const int* pair_start;
@@ -201,7 +206,16 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   }
   m.nM = int(m_anc.size());
   m.maxdepth = maxdepth;
-  if (m.nM > 65535) throw std::runtime_error("sparse inertia too large");
+  if (m.nM > 1280) throw std::runtime_error("sparse inertia too large (unsupported)");
+  if (maxdepth >= 64) throw std::runtime_error("dof chains deeper than 64 unsupported");
+  m.use_gen = (nv == gen::kNv) ? 1 : 0;
+  for (int i = 0; i < nv && m.use_gen; ++i) if (dof_parentid[i] != gen::kDofParent[i]) m.use_gen = 0;
+  std::memset(m.u_ancre, 0, sizeof(m.u_ancre));
+  for (int i = 0; i < nv; ++i)
+    for (int a = 0; a <= dof_depth[i]; ++a) {
+      const int j = m_anc[dof_madr[i] + a];  // ancestor with depth dof_depth[i] - a
+      m.u_ancre[dof_madr[i] + a] = uint16_t(dof_madr[j] + dof_depth[j]);
+    }
   std::vector<uint8_t> tri_a, tri_b;  // pair p = b(b+1)/2 + a, 0 <= a <= b < maxdepth
   for (int bb = 0; bb < maxdepth; ++bb) for (int a = 0; a <= bb; ++a) { tri_a.push_back(uint8_t(a)); tri_b.push_back(uint8_t(bb)); }
   std::vector<int32_t> desc_start(nv + 1, 0);
@@ -411,7 +425,7 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   {
     int c = 0;
     auto tk = [&](int n) { int r = c; c += pad4(n); return r; };
-    m.c_sx = tk(nv); m.c_sy = tk(nv); m.c_sD = tk(nv); m.c_sV = tk(m.ncb * 6); m.c_sW = tk(m.ncon * 6); m.c_sWb = tk(m.ncb * 6);
+    m.c_sx = tk(nv); m.c_sy = m.c_sD = 0; m.c_sV = tk(m.ncb * 6); m.c_sW = tk(m.ncon * 6); m.c_sWb = tk(m.ncb * 6);
     m.c_off = tk(m.ncon * 3); m.c_t1 = tk(m.ncon * 3); m.c_lf = tk(m.nlimit);
     m.c_end = c;
     o += std::max(pad4(nbody * 10), c);
