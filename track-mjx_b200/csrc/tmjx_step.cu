@@ -125,6 +125,13 @@ __device__ __forceinline__ float impedance(const float* par, float pos) {
   return imp;
 }
 
+// Block lock-step.  Every warp of a block simulates its own environment, but all of them walk the (large, ~400 KB)
+// step code phase by phase TOGETHER: a block barrier between phases keeps the warps inside the same few KB of code, so
+// the 32 KB L1.5 instruction cache and the model-table lines in L1 are fetched once per block instead of once per
+// warp (ncu: `stall_no_inst` was the top stall reason with free-running warps).  Barriers sit only in block-uniform
+// control flow; environment-dependent loops (CG termination, line search) are masked, never broken out of.
+__device__ __forceinline__ void phase_sync() { __syncthreads(); }
+
 // ---------------------------------------------------------------------------------------------- per-warp context
 struct Warp {
   const DevModel& m;
@@ -159,7 +166,86 @@ __device__ __forceinline__ float vdot(const float a[kNvSlots], const float b[kNv
 }
 
 // ---------------------------------------------------------------------------------------------- smooth dynamics
-// smooth.kinematics: level-parallel over bodies
+// ---- log-depth tree scans (ancestor doubling).  Lane l owns bodies l, l+32, l+64 (kBodySlots).
+constexpr int kBodySlots = 3;
+
+// inclusive prefix sum over the ancestors of every body: buf[b] <- sum of buf[a] for a on the path root..b (NC floats per body)
+template <int NC>
+__device__ __forceinline__ void scan_ancestors(const Warp& w, float* buf) {
+  const DevModel& m = w.m;
+  float acc[kBodySlots][NC];
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[s][k] = b < m.nbody ? buf[b * NC + k] : 0.f;
+  }
+  for (int r = 0; r < m.nround; ++r) {
+    float add[kBodySlots][NC];
+    bool on[kBodySlots];
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      const int b = w.lane + 32 * s;
+      const int a = b < m.nbody ? int(m.anc_pow[r * m.nbody + b]) : 0;
+      on[s] = a != 0;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) add[s][k] = on[s] ? buf[a * NC + k] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      if (!on[s]) continue;
+      const int b = w.lane + 32 * s;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) { acc[s][k] += add[s][k]; buf[b * NC + k] = acc[s][k]; }
+    }
+    __syncwarp();
+  }
+}
+
+// subtree sums: buf[b] <- sum of buf[c] over the subtree rooted at b (b >= 1), by doubling over descendant distance
+template <int NC>
+__device__ __forceinline__ void sum_subtrees(const Warp& w, float* buf) {
+  const DevModel& m = w.m;
+  float acc[kBodySlots][NC];
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[s][k] = b < m.nbody ? buf[b * NC + k] : 0.f;
+  }
+  for (int r = 0; r < m.nround; ++r) {
+    bool on[kBodySlots];
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      const int b = w.lane + 32 * s;
+      on[s] = false;
+      if (b < m.nbody) {
+        const int e0 = m.dsc_start[r * (m.nbody + 1) + b], e1 = m.dsc_start[r * (m.nbody + 1) + b + 1];
+        on[s] = e1 > e0;
+        for (int e = e0; e < e1; ++e) {
+          const float* src = buf + int(m.dsc_list[e]) * NC;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) acc[s][k] += src[k];
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      if (!on[s]) continue;
+      const int b = w.lane + 32 * s;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) buf[b * NC + k] = acc[s][k];
+    }
+    __syncwarp();
+  }
+}
+
+// smooth.kinematics.  Every body first composes its pose RELATIVE TO ITS PARENT (body offset, then its joints in order,
+// exactly the per-body arithmetic of mjx), recording joint anchors / axes in the parent frame; world poses then follow
+// from ancestor doubling (log2(depth) rounds of "compose with the ancestor 2^r levels up" instead of a 40-level walk),
+// and anchors / axes are mapped to the world with the parent's final pose.
 __device__ void kinematics(const Warp& w) {
   const DevModel& m = w.m;
   float* qpos = w.at(m.o_qpos);
@@ -168,55 +254,105 @@ __device__ void kinematics(const Warp& w) {
   float* xipos = w.at(m.o_big + m.a_xipos);
   float* anchor = w.at(m.o_big + m.a_anchor);
   float* axis = w.at(m.o_big + m.a_axis);
-  for (int lv = 0; lv < m.nlevel; ++lv) {
-    const int beg = m.lvl_start[lv], end = m.lvl_start[lv + 1];
-    for (int idx = beg + w.lane; idx < end; idx += 32) {
-      const int b = m.lvl_body[idx];
-      float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
-      if (b > 0) {
-        const int p = m.body_parent[b];
+  float P[kBodySlots][3], Q[kBodySlots][4];
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
+    if (b > 0 && b < m.nbody) {
+      pos[0] = m.body_pos[b * 3]; pos[1] = m.body_pos[b * 3 + 1]; pos[2] = m.body_pos[b * 3 + 2];
+      quat[0] = m.body_quat[b * 4]; quat[1] = m.body_quat[b * 4 + 1]; quat[2] = m.body_quat[b * 4 + 2]; quat[3] = m.body_quat[b * 4 + 3];
+      const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = ja + jj, qa = m.jnt_qposadr[j];
         float t[3];
-        rot(m.body_pos + b * 3, xquat + p * 4, t);
-        pos[0] = xpos[p * 3] + t[0]; pos[1] = xpos[p * 3 + 1] + t[1]; pos[2] = xpos[p * 3 + 2] + t[2];
-        qmul(xquat + p * 4, m.body_quat + b * 4, quat);
-        const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
-        for (int jj = 0; jj < jn; ++jj) {
-          const int j = ja + jj, qa = m.jnt_qposadr[j];
-          if (m.jnt_type[j] == kJntFree) {
-            anchor[j * 3] = qpos[qa]; anchor[j * 3 + 1] = qpos[qa + 1]; anchor[j * 3 + 2] = qpos[qa + 2];
-            axis[j * 3] = 0.f; axis[j * 3 + 1] = 0.f; axis[j * 3 + 2] = 1.f;
-            pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
-            quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
-            normalize4(quat);
-            qpos[qa + 3] = quat[0]; qpos[qa + 4] = quat[1]; qpos[qa + 5] = quat[2]; qpos[qa + 6] = quat[3];
-          } else {
-            float jp[3] = {m.jnt_pos[j * 3], m.jnt_pos[j * 3 + 1], m.jnt_pos[j * 3 + 2]};
-            float ja3[3] = {m.jnt_axis[j * 3], m.jnt_axis[j * 3 + 1], m.jnt_axis[j * 3 + 2]};
-            float an[3];
-            rot(jp, quat, t);
-            an[0] = t[0] + pos[0]; an[1] = t[1] + pos[1]; an[2] = t[2] + pos[2];
-            anchor[j * 3] = an[0]; anchor[j * 3 + 1] = an[1]; anchor[j * 3 + 2] = an[2];
-            rot(ja3, quat, t);
-            axis[j * 3] = t[0]; axis[j * 3 + 1] = t[1]; axis[j * 3 + 2] = t[2];
-            float sn, cs;
-            sincosf((qpos[qa] - m.jnt_qpos0[j]) * 0.5f, &sn, &cs);
-            const float ql[4] = {cs, ja3[0] * sn, ja3[1] * sn, ja3[2] * sn};
-            float q2[4];
-            qmul(quat, ql, q2);
-            quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
-            rot(jp, quat, t);
-            pos[0] = an[0] - t[0]; pos[1] = an[1] - t[1]; pos[2] = an[2] - t[2];
-          }
+        if (m.jnt_type[j] == kJntFree) {  // the tree root: its pose is absolute (parent = world)
+          pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
+          quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
+          normalize4(quat);
+          qpos[qa + 3] = quat[0]; qpos[qa + 4] = quat[1]; qpos[qa + 5] = quat[2]; qpos[qa + 6] = quat[3];
+          anchor[j * 3] = pos[0]; anchor[j * 3 + 1] = pos[1]; anchor[j * 3 + 2] = pos[2];
+          axis[j * 3] = 0.f; axis[j * 3 + 1] = 0.f; axis[j * 3 + 2] = 1.f;
+        } else {
+          const float jp[3] = {m.jnt_pos[j * 3], m.jnt_pos[j * 3 + 1], m.jnt_pos[j * 3 + 2]};
+          const float ja3[3] = {m.jnt_axis[j * 3], m.jnt_axis[j * 3 + 1], m.jnt_axis[j * 3 + 2]};
+          float an[3];
+          rot(jp, quat, t);
+          an[0] = t[0] + pos[0]; an[1] = t[1] + pos[1]; an[2] = t[2] + pos[2];
+          anchor[j * 3] = an[0]; anchor[j * 3 + 1] = an[1]; anchor[j * 3 + 2] = an[2];
+          rot(ja3, quat, t);
+          axis[j * 3] = t[0]; axis[j * 3 + 1] = t[1]; axis[j * 3 + 2] = t[2];
+          float sn, cs;
+          sincosf((qpos[qa] - m.jnt_qpos0[j]) * 0.5f, &sn, &cs);
+          const float ql[4] = {cs, ja3[0] * sn, ja3[1] * sn, ja3[2] * sn};
+          float q2[4];
+          qmul(quat, ql, q2);
+          quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+          rot(jp, quat, t);
+          pos[0] = an[0] - t[0]; pos[1] = an[1] - t[1]; pos[2] = an[2] - t[2];
         }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) P[s][k] = pos[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Q[s][k] = quat[k];
+    if (b < m.nbody) {
       xpos[b * 3] = pos[0]; xpos[b * 3 + 1] = pos[1]; xpos[b * 3 + 2] = pos[2];
       xquat[b * 4] = quat[0]; xquat[b * 4 + 1] = quat[1]; xquat[b * 4 + 2] = quat[2]; xquat[b * 4 + 3] = quat[3];
-      float t[3];
-      rot(m.body_ipos + b * 3, quat, t);
-      xipos[b * 3] = pos[0] + t[0]; xipos[b * 3 + 1] = pos[1] + t[1]; xipos[b * 3 + 2] = pos[2] + t[2];
+    }
+  }
+  __syncwarp();
+  for (int r = 0; r < m.nround; ++r) {
+    float Pa[kBodySlots][3], Qa[kBodySlots][4];
+    bool on[kBodySlots];
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      const int b = w.lane + 32 * s;
+      const int a = b < m.nbody ? int(m.anc_pow[r * m.nbody + b]) : 0;
+      on[s] = a != 0;
+      if (on[s]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Pa[s][k] = xpos[a * 3 + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Qa[s][k] = xquat[a * 4 + k];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      if (!on[s]) continue;
+      const int b = w.lane + 32 * s;
+      float t[3], q2[4];
+      rot(P[s], Qa[s], t);
+      qmul(Qa[s], Q[s], q2);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { P[s][k] = Pa[s][k] + t[k]; xpos[b * 3 + k] = P[s][k]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { Q[s][k] = q2[k]; xquat[b * 4 + k] = q2[k]; }
     }
     __syncwarp();
   }
+  // joint anchors / axes to the world frame with the parent body's pose; inertial frame origins
+  for (int j = w.lane; j < m.njnt; j += 32) {
+    if (m.jnt_type[j] == kJntFree) continue;
+    const int p = m.body_parent[m.jnt_body[j]];
+    float t[3];
+    rot(anchor + j * 3, xquat + p * 4, t);
+    anchor[j * 3] = xpos[p * 3] + t[0]; anchor[j * 3 + 1] = xpos[p * 3 + 1] + t[1]; anchor[j * 3 + 2] = xpos[p * 3 + 2] + t[2];
+    rot(axis + j * 3, xquat + p * 4, t);
+    axis[j * 3] = t[0]; axis[j * 3 + 1] = t[1]; axis[j * 3 + 2] = t[2];
+  }
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    if (b < m.nbody) {
+      float t[3];
+      rot(m.body_ipos + b * 3, Q[s], t);
+      xipos[b * 3] = P[s][0] + t[0]; xipos[b * 3 + 1] = P[s][1] + t[1]; xipos[b * 3 + 2] = P[s][2] + t[2];
+    }
+  }
+  __syncwarp();
 }
 
 // smooth.com_pos: COM of the moving tree (warp reduction), cinert per body, cdof per dof
@@ -280,8 +416,10 @@ __device__ void com_pos(const Warp& w, float com[3]) {
   __syncwarp();
 }
 
-// smooth.com_vel + the cacc scan of smooth.rne, one level-parallel sweep; then local cfrc, leaf-to-root gather,
-// qfrc_bias per dof (returned in registers)
+// smooth.com_vel + smooth.rne without level walks: body velocities / accelerations are prefix sums of per-body
+// increments over the ancestor path (two doubling scans), cdof_dot is evaluated per dof from its parent body's velocity
+// plus the earlier joints of the same body (mjx's in-body order), and the backward force accumulation is a subtree sum.
+// Returns qfrc_bias per dof in registers.
 __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
   const DevModel& m = w.m;
   const float* qvel = w.at(m.o_qvel);
@@ -290,67 +428,85 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
   float* cvel = w.at(m.o_big + m.a_cvel);
   float* cdd = w.at(m.o_big + m.a_cdofdot);
   float* cacc = w.at(m.o_big + m.a_cacc);
-  if (w.lane < 6) { cvel[w.lane] = 0.f; cacc[w.lane] = w.lane < 3 ? 0.f : -m.gravity[w.lane - 3]; }
-  __syncwarp();
-  for (int lv = 1; lv < m.nlevel; ++lv) {
-    const int beg = m.lvl_start[lv], end = m.lvl_start[lv + 1];
-    for (int idx = beg + w.lane; idx < end; idx += 32) {
-      const int b = m.lvl_body[idx], p = m.body_parent[b];
-      float cv[6], ca[6];
+  // per-body velocity increment: sum of cdof * qvel over the body's own dofs
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { cv[k] = cvel[p * 6 + k]; ca[k] = cacc[p * 6 + k]; }
-      const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
-      for (int jj = 0; jj < jn; ++jj) {
-        const int j = ja + jj, da = m.jnt_dofadr[j];
-        if (m.jnt_type[j] == kJntFree) {
-          for (int r = 0; r < 3; ++r)
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    if (b < m.nbody) {
+      float dv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int da = m.body_dofadr[b], dn = m.body_dofnum[b];
+      for (int d = da; d < da + dn; ++d) {
+        const float v = qvel[d];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { cv[k] += cdof[(da + r) * 6 + k] * qvel[da + r]; cdd[(da + r) * 6 + k] = 0.f; }
-          for (int r = 3; r < 6; ++r) {
-            float t[6];
-            motion_cross(cv, cdof + (da + r) * 6, t);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) cdd[(da + r) * 6 + k] = t[k];
-          }
-          for (int r = 3; r < 6; ++r)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) cv[k] += cdof[(da + r) * 6 + k] * qvel[da + r];
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) ca[k] += cdd[(da + r) * 6 + k] * qvel[da + r];
-        } else {
-          float t[6];
-          motion_cross(cv, cdof + da * 6, t);
-          const float v = qvel[da];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) { cdd[da * 6 + k] = t[k]; cv[k] += cdof[da * 6 + k] * v; ca[k] += t[k] * v; }
-        }
+        for (int k = 0; k < 6; ++k) dv[k] += cdof[d * 6 + k] * v;
       }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { cvel[b * 6 + k] = cv[k]; cacc[b * 6 + k] = ca[k]; }
+      for (int k = 0; k < 6; ++k) cvel[b * 6 + k] = dv[k];
     }
-    __syncwarp();
-  }
-  // local cfrc (in place of cacc)
-  for (int b = w.lane; b < m.nbody; b += 32) {
-    float f1[6], f2[6], f3[6];
-    inert_mul(cin + b * 10, cacc + b * 6, f1);
-    inert_mul(cin + b * 10, cvel + b * 6, f2);
-    motion_cross_force(cvel + b * 6, f2, f3);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = f1[k] + f3[k];
   }
   __syncwarp();
-  for (int lv = m.nlevel - 2; lv >= 1; --lv) {  // deterministic child gather
-    const int beg = m.lvl_start[lv], n = (m.lvl_start[lv + 1] - beg) * 6;
-    for (int t = w.lane; t < n; t += 32) {
-      const int b = m.lvl_body[beg + t / 6], k = t % 6;
-      float acc = cacc[b * 6 + k];
-      for (int c = m.child_start[b]; c < m.child_start[b + 1]; ++c) acc += cacc[m.child[c] * 6 + k];
-      cacc[b * 6 + k] = acc;
+  scan_ancestors<6>(w, cvel);
+  phase_sync();
+  // cdof_dot per dof
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    if (d < m.nv) {
+      const int b = m.dof_body[d], p = m.body_parent[b], j = m.dof_jnt[d], d0 = m.body_dofadr[b];
+      float cv[6], t[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cv[k] = cvel[p * 6 + k];
+      const bool is_free = m.jnt_type[j] == kJntFree;
+      const int r = d - m.jnt_dofadr[j];
+      // free joint: translations have cdof_dot = 0, the three rotations all see the velocity after the translations
+      const int upto = is_free ? (r < 3 ? d0 : d0 + 3) : d;
+      for (int e = d0; e < upto; ++e) {
+        const float v = qvel[e];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[k] += cdof[e * 6 + k] * v;
+      }
+      if (!(is_free && r < 3)) motion_cross(cv, cdof + d * 6, t);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cdd[d * 6 + k] = t[k];
     }
-    __syncwarp();
   }
+  __syncwarp();
+  // per-body acceleration increment, prefix sum, plus the root acceleration (-gravity) every body inherits
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    if (b < m.nbody) {
+      float da6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int da = m.body_dofadr[b], dn = m.body_dofnum[b];
+      for (int d = da; d < da + dn; ++d) {
+        const float v = qvel[d];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) da6[k] += cdd[d * 6 + k] * v;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = da6[k];
+    }
+  }
+  __syncwarp();
+  scan_ancestors<6>(w, cacc);
+  phase_sync();
+  // local cfrc (in place of cacc)
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    if (b < m.nbody) {
+      float ca[6], f1[6], f2[6], f3[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ca[k] = cacc[b * 6 + k] + (k < 3 ? 0.f : -m.gravity[k - 3]);
+      inert_mul(cin + b * 10, ca, f1);
+      inert_mul(cin + b * 10, cvel + b * 6, f2);
+      motion_cross_force(cvel + b * 6, f2, f3);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = f1[k] + f3[k];
+    }
+  }
+  __syncwarp();
+  sum_subtrees<6>(w, cacc);
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) {
     const int d = w.lane + 32 * q;
@@ -420,16 +576,7 @@ __device__ void build_m(const Warp& w) {
   float* L1 = w.at(m.o_big);
   float* L2 = w.at(m.o_big + m.nMpad);
   float* f = L2;  // M-build scratch, dead before L2 is written
-  for (int lv = m.nlevel - 2; lv >= 1; --lv) {
-    const int beg = m.lvl_start[lv], n = (m.lvl_start[lv + 1] - beg) * 10;
-    for (int t = w.lane; t < n; t += 32) {
-      const int b = m.lvl_body[beg + t / 10], k = t % 10;
-      float acc = crb[b * 10 + k];
-      for (int c = m.child_start[b]; c < m.child_start[b + 1]; ++c) acc += crb[m.child[c] * 10 + k];
-      crb[b * 10 + k] = acc;
-    }
-    __syncwarp();
-  }
+  sum_subtrees<10>(w, crb);
   for (int d = w.lane; d < m.nv; d += 32) {
     float t[6];
     inert_mul(crb + m.dof_body[d] * 10, cdof + d * 6, t);
@@ -471,67 +618,68 @@ __device__ void mul_m_raw(const Warp& w, const float* x, float out[kNvSlots]) {
 }
 
 // both L^T D L factorisations (smooth.factor_m of M, and of M + dt*diag(damping) for forward.euler) in one sweep.
-// Depth-lane mapping: lane d owns the entries whose COLUMN dof has depth d (d + 32 in the `hi` slot), for every row.
-// Row k is held in registers, the pivot entry l_a of each ancestor row travels by shuffle, the rank-1 update of row
-// `anc(k, a)` touches consecutive addresses (conflict-free) and -- because an entry is only ever read and written by
-// the one lane that owns its column depth -- the whole factorisation needs no barrier.  The a-loop is software
-// pipelined four rows at a time (all loads, then all FMAs, then all stores): rows of one pivot never alias.
-// kOff2 = compile-time distance between the two factors (0: read it from the model) so that the second factor is
-// addressed with an immediate offset.
-template <int kOff2>
+// The two matrices have the same structure, so they are STACKED in one warp: half-warp h = lane >> 4 works on matrix h,
+// lane i = lane & 15 of each half owns the entries whose COLUMN dof has depth 16 j + i (column block j), for every row.
+// Row k is held in registers (one register per column block), the pivot entry l_a of an ancestor row travels by one
+// half-warp shuffle, the rank-1 update of row anc(k, a) is one LDS / FFMA / STS for BOTH matrices and touches
+// consecutive addresses (conflict-free).  An entry is only ever read and written by the one lane that owns its
+// (matrix, column depth), so the factorisation needs no warp barrier; the division 1/D is shared by the two matrices.
+// The hot a-loop (a < 16: one column block) is software-pipelined four rows at a time; rows of one pivot never alias.
 __device__ void factor_dual(const Warp& w) {
   const DevModel& m = w.m;
-  float* L1 = w.at(m.o_big);
-  const int off2 = kOff2 ? kOff2 : m.nMpad, lane = w.lane;
-  float* pl = L1 - lane;  // entry (row r, column depth = lane) lives at pl[rowend(r)]
+  const int lane = w.lane, i = lane & 15, hbit = lane & 16;
+  float* ps = w.at(m.o_big) + (hbit ? m.nMpad : 0) - i;  // entry (row r, column depth 16 j + i) of my matrix: ps[rowend(r) - 16 j]
   for (int k = m.nv - 1; k >= 0; --k) {
+    if ((k & 7) == 7) phase_sync();
     const int c = m.u_depth[k], re = m.u_rowend[k];
-    float* rk = pl + re;
-    const bool hi = c >= 32;  // uniform
-    float l1 = 0.f, l2 = 0.f, h1 = 0.f, h2 = 0.f;
-    if (lane <= c) { l1 = rk[0]; l2 = rk[off2]; }
-    if (hi && lane + 32 <= c) { h1 = rk[-32]; h2 = rk[off2 - 32]; }
-    const float d1 = __shfl_sync(FULLMASK, hi ? h1 : l1, c & 31), d2 = __shfl_sync(FULLMASK, hi ? h2 : l2, c & 31);
-    const float inv1 = 1.f / d1, inv2 = 1.f / d2;
-    const float w1 = l1 * inv1, w2 = l2 * inv2;
+    float* rk = ps + re;
+    float lb0 = 0.f, lb1 = 0.f, lb2 = 0.f;
+    if (i <= c) lb0 = rk[0];
+    if (c >= 16 && i + 16 <= c) lb1 = rk[-16];
+    if (c >= 32 && i + 32 <= c) lb2 = rk[-32];
+    const float dsel = c < 16 ? lb0 : (c < 32 ? lb1 : lb2);
+    const float d = __shfl_sync(FULLMASK, dsel, (c & 15) | hbit);
+    const float inv = 1.f / d;
+    const float w0 = lb0 * inv, w1 = lb1 * inv, w2 = lb2 * inv;
     // scaled row + inverted diagonal (row k is not touched by its own rank-1 updates)
-    if (lane < c) { rk[0] = w1; rk[off2] = w2; }
-    else if (lane == c) { rk[0] = inv1; rk[off2] = inv2; }
-    int al = c - 1;
-    if (hi) {  // rows of depth >= 32 (deep chain tips only): they also own columns of depth >= 32
-      const float wh1 = h1 * inv1, wh2 = h2 * inv2;
-      if (lane + 32 < c) { rk[-32] = wh1; rk[off2 - 32] = wh2; }
-      else if (lane + 32 == c) { rk[-32] = inv1; rk[off2 - 32] = inv2; }
-      for (; al >= 32; --al) {
-        float* t = pl + int(m.u_ancre[re - al]);
-        const float a1 = __shfl_sync(FULLMASK, h1, al - 32), a2 = __shfl_sync(FULLMASK, h2, al - 32);
-        t[0] = fmaf(-a1, w1, t[0]); t[off2] = fmaf(-a2, w2, t[off2]);
-        if (lane + 32 <= al) { t[-32] = fmaf(-a1, wh1, t[-32]); t[off2 - 32] = fmaf(-a2, wh2, t[off2 - 32]); }
-      }
+    if (i < c) rk[0] = w0; else if (i == c) rk[0] = inv;
+    if (c >= 16) { if (i + 16 < c) rk[-16] = w1; else if (i + 16 == c) rk[-16] = inv; }
+    if (c >= 32) { if (i + 32 < c) rk[-32] = w2; else if (i + 32 == c) rk[-32] = inv; }
+    int al = c - 1, ti = re - al;  // u_ancre[ti] = row end of the ancestor at depth al
+    for (; al >= 32; --al, ++ti) {  // deep chain tips only: three column blocks
+      float* t = ps + int(m.u_ancre[ti]);
+      const float a = __shfl_sync(FULLMASK, lb2, (al & 15) | hbit);
+      t[0] = fmaf(-a, w0, t[0]);
+      t[-16] = fmaf(-a, w1, t[-16]);
+      if (i + 32 <= al) t[-32] = fmaf(-a, w2, t[-32]);
     }
-    int ti = re - al;  // u_ancre[ti + u] = row end of the ancestor at depth al - u
-    for (; al >= 3; al -= 4, ti += 4) {
-      float* t0 = pl + int(m.u_ancre[ti]); float* t1 = pl + int(m.u_ancre[ti + 1]); float* t2 = pl + int(m.u_ancre[ti + 2]);
-      float* t3 = pl + int(m.u_ancre[ti + 3]);
-      const float a10 = __shfl_sync(FULLMASK, l1, al), a20 = __shfl_sync(FULLMASK, l2, al);
-      const float a11 = __shfl_sync(FULLMASK, l1, al - 1), a21 = __shfl_sync(FULLMASK, l2, al - 1);
-      const float a12 = __shfl_sync(FULLMASK, l1, al - 2), a22 = __shfl_sync(FULLMASK, l2, al - 2);
-      const float a13 = __shfl_sync(FULLMASK, l1, al - 3), a23 = __shfl_sync(FULLMASK, l2, al - 3);
-      const bool p0 = lane <= al, p1 = lane <= al - 1, p2 = lane <= al - 2, p3 = lane <= al - 3;
-      float v10, v20, v11, v21, v12, v22, v13, v23;
-      if (p0) { v10 = t0[0]; v20 = t0[off2]; }
-      if (p1) { v11 = t1[0]; v21 = t1[off2]; }
-      if (p2) { v12 = t2[0]; v22 = t2[off2]; }
-      if (p3) { v13 = t3[0]; v23 = t3[off2]; }
-      if (p0) { t0[0] = fmaf(-a10, w1, v10); t0[off2] = fmaf(-a20, w2, v20); }
-      if (p1) { t1[0] = fmaf(-a11, w1, v11); t1[off2] = fmaf(-a21, w2, v21); }
-      if (p2) { t2[0] = fmaf(-a12, w1, v12); t2[off2] = fmaf(-a22, w2, v22); }
-      if (p3) { t3[0] = fmaf(-a13, w1, v13); t3[off2] = fmaf(-a23, w2, v23); }
+    for (; al >= 16; --al, ++ti) {  // two column blocks
+      float* t = ps + int(m.u_ancre[ti]);
+      const float a = __shfl_sync(FULLMASK, lb1, (al & 15) | hbit);
+      const float v0 = t[0];
+      t[0] = fmaf(-a, w0, v0);
+      if (i + 16 <= al) t[-16] = fmaf(-a, w1, t[-16]);
+    }
+    for (; al >= 3; al -= 4, ti += 4) {  // one column block, four rows in flight
+      float* t0 = ps + int(m.u_ancre[ti]); float* t1 = ps + int(m.u_ancre[ti + 1]); float* t2 = ps + int(m.u_ancre[ti + 2]);
+      float* t3 = ps + int(m.u_ancre[ti + 3]);
+      const float a0 = __shfl_sync(FULLMASK, lb0, al | hbit), a1 = __shfl_sync(FULLMASK, lb0, (al - 1) | hbit);
+      const float a2 = __shfl_sync(FULLMASK, lb0, (al - 2) | hbit), a3 = __shfl_sync(FULLMASK, lb0, (al - 3) | hbit);
+      const bool p0 = i <= al, p1 = i <= al - 1, p2 = i <= al - 2, p3 = i <= al - 3;
+      float v0, v1, v2, v3;
+      if (p0) v0 = t0[0];
+      if (p1) v1 = t1[0];
+      if (p2) v2 = t2[0];
+      if (p3) v3 = t3[0];
+      if (p0) t0[0] = fmaf(-a0, w0, v0);
+      if (p1) t1[0] = fmaf(-a1, w0, v1);
+      if (p2) t2[0] = fmaf(-a2, w0, v2);
+      if (p3) t3[0] = fmaf(-a3, w0, v3);
     }
     for (; al >= 0; --al, ++ti) {
-      float* t = pl + int(m.u_ancre[ti]);
-      const float a1 = __shfl_sync(FULLMASK, l1, al), a2 = __shfl_sync(FULLMASK, l2, al);
-      if (lane <= al) { t[0] = fmaf(-a1, w1, t[0]); t[off2] = fmaf(-a2, w2, t[off2]); }
+      float* t = ps + int(m.u_ancre[ti]);
+      const float a = __shfl_sync(FULLMASK, lb0, al | hbit);
+      if (i <= al) t[0] = fmaf(-a, w0, t[0]);
     }
   }
   __syncwarp();  // consumers (solves, M products) use a dof-lane mapping
@@ -890,14 +1038,18 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q]; mv[q] = -grad[q]; }
   }
   const float scale = m.meaninertia_scale;
-  for (int iter = 0;; ++iter) {
-    if (m.iterations != 1) {
+  // The iteration count is block-uniform (phase barriers inside): an environment whose solver has terminated
+  // (solver.py's while_loop cond) is masked for the remaining rounds instead of breaking out.
+  const int max_iter = m.iterations != 1 ? m.iterations : 1;
+  bool active = true;
+  for (int iter = 0; iter < max_iter; ++iter) {
+    phase_sync();
+    if (active && m.iterations != 1) {
       const float improvement = (prev_cost - cost) / scale;
       const float gradient = sqrtf(vdot(grad, grad)) / scale;
-      if (iter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
-    } else if (iter >= 1) {
-      break;
+      if (improvement < m.tolerance || gradient < m.tolerance) active = false;
     }
+    if (active) {
     // ---- _linesearch
     const float smag = sqrtf(vdot(search, search)) * scale;
     const float gtol = m.tolerance * m.ls_tolerance * smag;
@@ -961,6 +1113,9 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
 #pragma unroll
       for (int k = 0; k < kRowSlots; ++k) Jaref[k] += jv[k] * alpha;
     }
+    }
+    phase_sync();
+    if (active) {
     // ---- body: update + Polak-Ribiere
     float pg[kNvSlots], pMg[kNvSlots];
 #pragma unroll
@@ -974,6 +1129,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     beta = fmaxf(0.f, beta);
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q] + beta * search[q]; mv[q] = -grad[q] + beta * mv[q]; }
+    }
   }
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) { so.qacc[q] = qacc[q]; so.qfc[q] = qfc[q]; }
@@ -989,21 +1145,28 @@ struct FwdOut {
 
 __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   const DevModel& m = w.m;
+  phase_sync();
   kinematics(w);
+  phase_sync();
   com_pos(w, fo.com);
+  phase_sync();
   com_vel_rne(w, fo.bias);
+  phase_sync();
   passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
   __syncwarp();
   build_m(w);
+  phase_sync();
   float Maw[kNvSlots];
   mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  if (m.use_gen) factor_dual<gen::kNMpad>(w); else factor_dual<0>(w);
+  factor_dual(w);
+  phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
   solve_ld(w, w.at(m.o_big), fo.qas);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
+  phase_sync();
   solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
   vput(w, w.at(m.o_warm), fo.so.qacc);
   __syncwarp();
@@ -1152,12 +1315,19 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
   const DevModel& m = a.m;
   const DevTask& t = *a.task;
   const TmjxTaskConfig& cfg = t.cfg;
-  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = kWPB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Warp w{m, smem + size_t(warp) * m.smem_floats, lane, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) { w.dep[q] = m.depth_me[q * 32 + lane]; w.rend[q] = m.rowend_me[q * 32 + lane]; }
   const int nu = m.nu, nobs = t.obs_size, W = cfg.var_window_size;
-  for (int e = blockIdx.x * wpb + warp; e < a.n_env; e += gridDim.x * wpb) {
+  // Environment e belongs to block e % gridDim.x (so a partly filled last round is spread over all SMs).  The number
+  // of rounds is block-uniform; a warp without an environment in the last round recomputes the block's last one
+  // (reads only, nothing is written) so that it keeps arriving at the phase barriers.
+  const int G = gridDim.x, count = (a.n_env - int(blockIdx.x) + G - 1) / G, nrounds = (count + wpb - 1) / wpb;
+  for (int rd = 0; rd < nrounds; ++rd) {
+    const int slot = rd * wpb + warp;
+    const bool live = slot < count;
+    const int e = (live ? slot : count - 1) * G + int(blockIdx.x);
     // ---- stage the persistent state
     float* qpos = w.at(m.o_qpos);
     float* qvel = w.at(m.o_qvel);
@@ -1187,7 +1357,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
     __syncwarp();
 
     FwdOut fo;
-    float* dbg_dist = a.out.dbg_contact_dist ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
+    float* dbg_dist = (live && a.out.dbg_contact_dist) ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
     if (kStep) {
       for (int f = 0; f < m.n_frames; ++f) {
         forward(w, fo, f == m.n_frames - 1 ? dbg_dist : nullptr);
@@ -1197,6 +1367,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
       forward(w, fo, dbg_dist);
     }
 
+    if (live) {
     // ---- NaN scan over the state this build materialises (stand-in for ravel_pytree(data), :290-293)
     bool bad = isnan(time);
     for (int i = lane; i < m.nq; i += 32) bad |= isnan(qpos[i]);
@@ -1393,6 +1564,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
       for (int i = lane; i < nu; i += 32) a.st.first_prev_ctrl[size_t(e) * nu + i] = 0.f;
       if (lane == 0) { a.st.first_time[e] = time; a.st.steps[e] = 0.f; a.st.truncation[e] = 0.f; }
     }
+    }  // live
     __syncwarp();
   }
 }
@@ -1421,7 +1593,7 @@ struct TmjxModel {
   uint16_t* d_u16 = nullptr;
   uint8_t* d_u8 = nullptr;
   float* d_f32 = nullptr;
-  int device = 0, sm_count = 0, envs_per_block = 7, max_blocks_per_sm = 1, variant = 0;
+  int device = 0, sm_count = 0, envs_per_block = 12, max_blocks_per_sm = 1;
   size_t smem_per_block = 0;
   TmjxTaskConfig cfg;
 };
@@ -1474,20 +1646,23 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
   // 7 warps x 2 blocks = 14 resident envs per SM when the per-env slice allows it, else 4 warps x up to 3 blocks
-  m->envs_per_block = (2 * (7 * per_env + 1024) <= prop.sharedMemPerMultiprocessor) ? 7 : 4;
-  int variant = 0;
-  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { m->envs_per_block = atoi(e) == 7 ? 7 : 4; variant = atoi(e); }  // tuning knob
-  if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                // tuning knob
+  // one block per SM, all of its warps in lock-step (phase_sync): 12 or 14 resident environments per SM
+  m->envs_per_block = 14;
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { const int v = atoi(e); m->envs_per_block = (v == 12 || v == 4) ? v : 14; }  // tuning knob
+  if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                                                  // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
-  m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
-  if (m->envs_per_block == 7) m->max_blocks_per_sm = std::min(m->max_blocks_per_sm, 2);
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
-  m->variant = variant;
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->smem_per_block)));
+  m->max_blocks_per_sm = m->envs_per_block == 4 ? int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024))) : 1;
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 12)));
+  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 12)));
+  if (per_env * 14 <= prop.sharedMemPerBlockOptin) {
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
+  } else if (m->envs_per_block == 14) {
+    m->envs_per_block = 12; m->smem_per_block = per_env * 12;
+  }
   *out = m;
   return TMJX_OK;
 }
@@ -1572,8 +1747,8 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   const int epb = m->envs_per_block;
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
-  if (kStep && m->variant == 44) tmjx_env_kernel<true, 4, 4><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
-  else if (epb == 7) tmjx_env_kernel<kStep, 7, 2><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  if (epb == 14) tmjx_env_kernel<kStep, 14, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  else if (epb == 12) tmjx_env_kernel<kStep, 12, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   else tmjx_env_kernel<kStep, 4, 3><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   CU(cudaGetLastError());
   return TMJX_OK;

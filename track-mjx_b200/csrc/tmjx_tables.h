@@ -45,6 +45,11 @@ struct DevModel {
   const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *lvl_start, *lvl_body, *child_start,
       *child;
   const float *body_pos, *body_quat, *body_ipos, *body_iquat, *body_inertia, *body_mass, *body_tree_mass;
+  /* log-depth tree scans: anc_pow[r * nbody + b] = ancestor of body b at distance 2^r (0 = none / world);
+   * dsc_list[dsc_start[r * (nbody + 1) + b] ..) = descendants of b at distance exactly 2^r (b >= 1) */
+  int nround;
+  const uint8_t *anc_pow, *dsc_list;
+  const uint16_t* dsc_start;
   // ---- per joint
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_body;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_qpos0, *jnt_springref;
@@ -177,6 +182,29 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     for (int c = 1; c < nbody; ++c) if (body_parent[c] == i) child.push_back(c);
   }
   child_start[nbody] = int(child.size());
+
+  // ---- ancestor / descendant tables for the doubling scans
+  int nround = 0;
+  while ((1 << nround) < nlevel) ++nround;
+  m.nround = nround;
+  std::vector<uint8_t> anc_pow(size_t(std::max(nround, 1)) * nbody, 0), dsc_list;
+  std::vector<uint16_t> dsc_start;
+  for (int r = 0; r < nround; ++r) {
+    for (int i = 0; i < nbody; ++i) {
+      int a = i;
+      for (int s = 0; s < (1 << r) && a > 0; ++s) a = body_parent[a];
+      anc_pow[size_t(r) * nbody + i] = uint8_t(depth[i] >= (1 << r) ? a : 0);
+    }
+    for (int i = 0; i <= nbody; ++i) {
+      dsc_start.push_back(uint16_t(dsc_list.size()));
+      if (i == 0 || i == nbody) continue;
+      for (int c = i + 1; c < nbody; ++c)
+        if (depth[c] - depth[i] == (1 << r) && anc_pow[size_t(r) * nbody + c] == i) dsc_list.push_back(uint8_t(c));
+    }
+  }
+  if (dsc_start.empty()) dsc_start.push_back(0);
+  if (dsc_list.empty()) dsc_list.push_back(0);
+  if (nbody > 255) throw std::runtime_error("more than 255 bodies unsupported");
 
   // ---- moving tree
   int tree_root = -1;
@@ -396,6 +424,8 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   PI(dof_body, dof_bodyid); PI(dof_jnt, dof_jntid); PI(dof_madr, dof_madr); PI(dof_depth, dof_depth); PI(dof_limit, dof_limit);
   PI(dof_qadr, dof_qadr);
   PF(dof_armature, b.f32("dof_armature")); PF(dof_damping, b.f32("dof_damping"));
+  P8(anc_pow, anc_pow); P8(dsc_list, dsc_list);
+  m.dsc_start = TMJX_OFF(uint16_t, push(t.u16, dsc_start));
   P8(m_anc, m_anc); P8(m_row, m_row); P8(m_col, m_col); P8(tri_a, tri_a); P8(tri_b, tri_b);
   m.dmask = TMJX_OFF(uint32_t, push(t.i32, dmask)); m.amask = TMJX_OFF(uint32_t, push(t.i32, amask));
   PI(rowend_me, rowend_me); PI(depth_me, depth_me);
@@ -455,6 +485,8 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   RF(jnt_pos); RF(jnt_axis); RF(jnt_stiffness); RF(jnt_qpos0); RF(jnt_springref);
   RI(dof_body); RI(dof_jnt); RI(dof_madr); RI(dof_depth); RI(dof_limit); RI(dof_qadr);
   RF(dof_armature); RF(dof_damping);
+  R8(anc_pow); R8(dsc_list);
+  m.dsc_start = d16 + reinterpret_cast<uintptr_t>(m.dsc_start);
   R8(m_anc); R8(m_row); R8(m_col); R8(tri_a); R8(tri_b);
   m.dmask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dmask);
   m.amask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.amask);
