@@ -143,7 +143,9 @@ def run_ours(args, rank, world, local_rank):
     import torch
 
     from track_mjx_b200.env import MultiClipTracking, wrap
+    from track_mjx_b200.sharding import Shard, max_over_ranks, reduce_episode_stats
 
+    shard = Shard(rank, world, ENVS_PER_GPU * world)   # weak scaling: 4096 envs per GPU, contiguous global env ids per rank
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -153,7 +155,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     walker, clips, config = build_env_pieces(1)
     env = wrap(MultiClipTracking(clips, walker, config.RewardConfig(), num_envs=ENVS_PER_GPU, device=local_rank, **config.DEFAULT_ENV_ARGS))
-    state = env.reset(1000 + rank)
+    state = env.reset(shard.seed(1000))
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
     n_act = min(K + W, 64)
@@ -188,12 +190,8 @@ def run_ours(args, rank, world, local_rank):
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
-    stats = torch.stack([rew_sum, done_sum]).double()
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)   # episode statistics over NVLink (the only collective of the env path)
-    max_ms = float(t.item())
+    max_ms = max_over_ranks(dev_ms, dev, shard)                      # device time, max over ranks
+    stats = reduce_episode_stats(rew_sum, done_sum, K, shard)        # SUM over NVLink: the only collective of the env path
     value = ENVS_PER_GPU * world * K / (max_ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step
@@ -221,10 +219,7 @@ def run_ours(args, rank, world, local_rank):
         state = e2e_step(i, state)
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = ENVS_PER_GPU * world * K / float(te.item())
+    e2e_value = ENVS_PER_GPU * world * K / max_over_ranks(e2e_s, dev, shard)
     h2d = ENVS_PER_GPU * env.action_size * 4
     d2h = ENVS_PER_GPU * (obs_dim + 2) * 4
 
@@ -267,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "wall_s_timed_region": wall,
-        "episode_stats": {"mean_reward": float(stats[0].item()) / (ENVS_PER_GPU * world * K), "done_frac": float(stats[1].item()) / (ENVS_PER_GPU * world * K)},
+        "episode_stats": stats,
     }
     print(json.dumps(out), flush=True)
     if dist is not None:

@@ -1646,22 +1646,22 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
   // 7 warps x 2 blocks = 14 resident envs per SM when the per-env slice allows it, else 4 warps x up to 3 blocks
-  // one block per SM, all of its warps in lock-step (phase_sync): 12 or 14 resident environments per SM
+  // one block per SM, all of its 14 warps in lock-step (phase_sync); models whose per-env slice is too large for 14
+  // resident environments fall back to blocks of 4
   m->envs_per_block = 14;
-  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { const int v = atoi(e); m->envs_per_block = (v == 12 || v == 4) ? v : 14; }  // tuning knob
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { const int v = atoi(e); m->envs_per_block = v == 4 ? 4 : 14; }  // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                                                  // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = m->envs_per_block == 4 ? int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024))) : 1;
   CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
   CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 12)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 12)));
   if (per_env * 14 <= prop.sharedMemPerBlockOptin) {
     CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
     CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
   } else if (m->envs_per_block == 14) {
-    m->envs_per_block = 12; m->smem_per_block = per_env * 12;
+    m->envs_per_block = 4; m->smem_per_block = per_env * 4;
+    m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
   }
   *out = m;
   return TMJX_OK;
@@ -1748,7 +1748,6 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
   if (epb == 14) tmjx_env_kernel<kStep, 14, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
-  else if (epb == 12) tmjx_env_kernel<kStep, 12, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   else tmjx_env_kernel<kStep, 4, 3><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   CU(cudaGetLastError());
   return TMJX_OK;
