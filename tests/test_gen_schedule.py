@@ -35,5 +35,28 @@ def test_generated_solve_random_trees():
         _check(G.Tree(parent), nv)
 
 
+def _check_factor(tree, seed):
+    rng = np.random.default_rng(seed)
+    M = G.random_tree_spd(tree, rng)
+    M2 = M + np.diag(rng.uniform(0.0, 0.3, tree.nv))
+    s1, s2 = G.sparse_from_dense(tree, M), G.sparse_from_dense(tree, M2)
+    L1, L2 = G.run_factor_ir(G.build_factor_ir(tree), tree, s1.astype(np.float32), s2.astype(np.float32))
+    for got, ref in ((L1, G.factor_ref(tree, s1)), (L2, G.factor_ref(tree, s2))):
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-5
+
+
+def test_generated_factor_matches_reference_rodent():
+    t = G.rodent_tree()
+    for seed in range(2):
+        _check_factor(t, seed)
+
+
+def test_generated_factor_random_trees():
+    rng = np.random.default_rng(11)
+    for nv in (1, 5, 20, 40, 64):
+        parent = [-1] + [int(rng.integers(max(0, i - 3), i)) for i in range(1, nv)]
+        _check_factor(G.Tree(parent), nv)
+
+
 def test_committed_header_is_current():
     assert open(G.OUT).read() == G.emit_cuda(G.rodent_tree())

@@ -101,6 +101,114 @@ def build_solve_ir(t: Tree):
     return ir
 
 
+# ------------------------------------------------------------------------------------------------ factorisation IR
+# Stacked dual L^T D L: half-warp h = lane >> 4 owns matrix h (stored at L + h * off2), lane i = lane & 15 owns the
+# entries whose column dof has depth 16 j + i (column block j).  Per-lane pointer ps = L + h * off2 - i, so entry
+# (row r, column depth 16 j + i) is ps[rowend(r) - 16 j].
+#   ("ld", reg, imm, mask)          reg = ps[imm] on lanes in mask, 0 elsewhere
+#   ("shflh", dst, src, l15)        dst = src[l15 | (lane & 16)]           (half-warp broadcast)
+#   ("rcp", dst, src) / ("mul", dst, a, b)
+#   ("st", imm, reg, mask)          ps[imm] = reg on lanes in mask
+#   ("fnma_reg", dst, a, w, mask)   dst = dst - a * w on lanes in mask (dst: a row register)
+#   ("sync",)                       block phase barrier (instruction-cache lock-step)
+def half_mask(n):
+    """lanes i < n of both half-warps (n in 0..16)."""
+    n = max(0, min(16, n))
+    m16 = (1 << n) - 1
+    return m16 | (m16 << 16)
+
+
+def chains_descending(t: Tree):
+    """Maximal runs k, k-1, ... with parent(k) == k - 1, listed from the highest dof id down (every descendant chain of a
+    chain comes before it, which is all the elimination order needs)."""
+    out, k = [], t.nv - 1
+    while k >= 0:
+        run = [k]
+        while t.parent[run[-1]] == run[-1] - 1 and run[-1] - 1 >= 0:
+            run.append(run[-1] - 1)
+        out.append(run)
+        k = run[-1] - 1
+    return out
+
+
+def build_factor_ir(t: Tree):
+    """Chain-at-a-time elimination: the rows a chain's pivots touch (the chain itself + the ancestors of its top end) are
+    loaded into registers once, every pivot of the chain then updates them with shuffle + FMA only, and they are stored
+    back once -- instead of one shared-memory load/store per (pivot, ancestor row)."""
+    ir = []
+    npiv = 0
+    for run in chains_descending(t):
+        bottom = run[-1]
+        rows = list(run) + t.anc[bottom]          # every row this chain reads or updates
+        ir.append(("sync",))
+        for r in rows:
+            for j in range(t.depth[r] // 16 + 1):
+                ir.append(("ld", f"r{r}_{j}", t.rowend[r] - 16 * j, half_mask(t.depth[r] - 16 * j + 1)))
+        for k in run:
+            npiv += 1
+            if npiv % 8 == 0:
+                ir.append(("sync",))
+            c, re = t.depth[k], t.rowend[k]
+            nb = c // 16 + 1
+            ir.append(("shflh", "d", f"r{k}_{c >> 4}", c & 15))
+            ir.append(("rcp", "inv", "d"))
+            for j in range(nb):
+                ir.append(("mul", f"w{j}", f"r{k}_{j}", "inv"))
+            for j in range(nb):
+                lo = half_mask(c - 16 * j)            # columns with depth < c
+                if lo:
+                    ir.append(("st", re - 16 * j, f"w{j}", lo))
+            jd = c >> 4
+            ir.append(("st", re - 16 * jd, "inv", half_mask((c & 15) + 1) & ~half_mask(c & 15)))
+            chain = [k] + t.anc[k]                    # chain[a] = a-th ancestor, depth c - a
+            for al in range(c - 1, -1, -1):
+                row = chain[c - al]
+                ir.append(("shflh", "a", f"r{k}_{al >> 4}", al & 15))
+                for j in range(al // 16 + 1):
+                    ir.append(("fnma_reg", f"r{row}_{j}", "a", f"w{j}", half_mask(al - 16 * j + 1)))
+        for r in t.anc[bottom]:                       # ancestors of the chain: updated, not yet eliminated
+            for j in range(t.depth[r] // 16 + 1):
+                ir.append(("st", t.rowend[r] - 16 * j, f"r{r}_{j}", half_mask(t.depth[r] - 16 * j + 1)))
+    return ir
+
+
+def run_factor_ir(ir, t: Tree, M1: np.ndarray, M2: np.ndarray):
+    """numpy interpreter of the stacked factorisation; M1 / M2: sparse rows [nM]; returns the two factors."""
+    off2 = (t.nM + 3) & ~3
+    pad = 64
+    mem = np.full(pad + 2 * off2 + pad, np.nan, np.float32)
+    mem[pad:pad + t.nM] = M1
+    mem[pad + off2:pad + off2 + t.nM] = M2
+    lanes = np.arange(32)
+    base = pad + (lanes >> 4) * off2 - (lanes & 15)
+    regs = {}
+    for op in ir:
+        if op[0] == "sync":
+            continue
+        if op[0] == "ld":
+            _, r, imm, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            regs[r] = np.where(act, mem[base + imm], np.float32(0)).astype(np.float32)
+        elif op[0] == "shflh":
+            _, dst, src, l15 = op
+            regs[dst] = regs[src][l15 | (lanes & 16)].astype(np.float32)
+        elif op[0] == "rcp":
+            regs[op[1]] = (np.float32(1) / regs[op[2]]).astype(np.float32)
+        elif op[0] == "mul":
+            regs[op[1]] = (regs[op[2]] * regs[op[3]]).astype(np.float32)
+        elif op[0] == "st":
+            _, imm, r, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            mem[(base + imm)[act]] = regs[r][act]
+        elif op[0] == "fnma_reg":
+            _, dst, a, w, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            regs[dst] = np.where(act, (regs[dst] - regs[a] * regs[w]).astype(np.float32), regs[dst])
+        else:
+            raise ValueError(op)
+    return mem[pad:pad + t.nM].copy(), mem[pad + off2:pad + off2 + t.nM].copy()
+
+
 def lane_tables(t: Tree):
     nslot = (t.nv + 31) // 32
     tabs = {}
@@ -229,6 +337,41 @@ def emit_cuda(t: Tree) -> str:
     w("  V3 r; r.a = x0; r.b = x1; r.c = x2;")
     w("  return r;")
     w("}")
+    w("// Both L^T D L factorisations (M at L, M + dt diag(damping) at L + kNMpad), stacked half-warp per matrix; see")
+    w("// factor_dual in tmjx_step.cu for the loop form of the same schedule (used for other trees).")
+    w("__device__ __noinline__ void factor_dual(float* __restrict__ L, int lane) {")
+    w("  const unsigned lb = 1u << lane;")
+    w("  const int hbit = lane & 16;")
+    w("  float* ps = L + (hbit ? kNMpad : 0) - (lane & 15);")
+    fir = build_factor_ir(t)
+    w("  float w0 = 0.f, w1 = 0.f, w2 = 0.f, d, inv, a;")
+    declared = set()
+    for op in fir:
+        if op[0] == "sync":
+            w("  __syncthreads();")
+        elif op[0] == "ld":
+            _, r, imm, mask = op
+            decl = "" if r in declared else "float "
+            declared.add(r)
+            if mask == full:
+                w(f"  {decl}{r} = ps[{imm}];")
+            else:
+                w(f"  {decl}{r} = (lb & 0x{mask:08x}u) ? ps[{imm}] : 0.f;")
+        elif op[0] == "shflh":
+            w(f"  {op[1]} = __shfl_sync(0xffffffffu, {op[2]}, {op[3]} | hbit);")
+        elif op[0] == "rcp":
+            w(f"  {op[1]} = 1.f / {op[2]};")
+        elif op[0] == "mul":
+            w(f"  {op[1]} = {op[2]} * {op[3]};")
+        elif op[0] == "st":
+            _, imm, r, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}ps[{imm}] = {r};")
+        elif op[0] == "fnma_reg":
+            _, dst, a_, w_, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}{dst} = fmaf(-{a_}, {w_}, {dst});")
+    w("}")
     w("#endif  // __CUDACC__")
     w("}}  // namespace tmjx::gen")
     w("#endif  // TMJX_GEN_TREE_CUH_")
@@ -249,8 +392,10 @@ def main():
     with open(OUT, "w") as f:
         f.write(src)
     ir = build_solve_ir(t)
+    fir = build_factor_ir(t)
     print(f"wrote {OUT}: nv {t.nv} nM {t.nM} maxdepth {t.maxdepth}, solve IR {len(ir)} ops "
-          f"({sum(1 for x in ir if x[0] == 'shfl')} shuffles)")
+          f"({sum(1 for x in ir if x[0] == 'shfl')} shuffles), factor IR {len(fir)} ops "
+          f"({sum(1 for x in fir if x[0] == 'fnma_reg')} row updates, {sum(1 for x in fir if x[0] in ('ld', 'st'))} LDS/STS)")
 
 
 if __name__ == "__main__":

@@ -1159,7 +1159,7 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   float Maw[kNvSlots];
   mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  factor_dual(w);
+  if (m.use_gen) { gen::factor_dual(w.at(m.o_big), w.lane); __syncwarp(); } else factor_dual(w);
   phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
@@ -1653,7 +1653,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                                                  // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
-  m->max_blocks_per_sm = m->envs_per_block == 4 ? int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024))) : 1;
+  m->max_blocks_per_sm = m->envs_per_block == 14 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
   CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
   CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
   if (per_env * 14 <= prop.sharedMemPerBlockOptin) {
