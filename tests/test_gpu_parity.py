@@ -120,6 +120,30 @@ def test_control_step_parity_and_drift(walker, clips2):
     g.close()
 
 
+@pytest.mark.parametrize("iterations,nf", [(1, 1), (4, 1), (3, 4)])
+def test_newton_solver_parity(walker, clips2, iterations, nf):
+    """solver="newton" (BASELINE configs[4]): H = M + J^T D J assembled in the tree-sparse layout, factored and solved
+    on the GPU, against the oracle's dense Newton (solver.py Newton branch) on contact-rich states."""
+    n = 64
+    st = rollout_states(walker, clips2, n, 6, 0.1, seed=11)
+    cfg = make_cfg(walker, solver="newton", iterations=iterations, ls_iterations=6, physics_steps_per_control_step=nf)
+    o32, o64 = Oracle(walker.blob, cfg, clips2, dtype=np.float32), Oracle(walker.blob, cfg, clips2, dtype=np.float64)
+    g = Stepper(walker.blob, cfg, clips2, n, 0, debug=True)
+    a, b = o32.alloc(n), o64.alloc(n)
+    for buf in (a, b, g.buf):
+        common.put(buf, st)
+    act = (0.1 * np.random.default_rng(12).normal(size=(n, walker.nu))).astype(np.float32)
+    o32.step(a, act)
+    o64.step(b, act)
+    g.step(torch.from_numpy(act).cuda())
+    gb = common.get(g.buf)
+    assert (a["dbg_contact_dist"] < 0).sum() > n          # contacts are active: the Hessian has contact blocks
+    for k in ("qpos", "qvel", "dbg_qacc", "dbg_qfrc_constraint", "obs"):
+        close(gb, a, b, k, 2e-4 if k in ("dbg_qacc", "dbg_qfrc_constraint") else 2e-5, factor=10.0)
+    assert (gb["done"] == a["done"]).all() and (gb["cur_frame"] == a["cur_frame"]).all()
+    g.close()
+
+
 def test_done_flags_and_frames_bit_exact_many_envs(walker, clips2):
     """1024 envs, mixed regimes (some terminating): flags, frame indices and integer state are bit-exact.
 
@@ -234,8 +258,9 @@ def test_c_abi_error_paths(walker, clips2):
     assert lib.tmjx_model_create(walker.blob, len(walker.blob), C.byref(bad), 0, C.byref(h)) == -1
     assert b"abi" in lib.tmjx_last_error()
     assert lib.tmjx_model_create(walker.blob[:100], 100, C.byref(cfg), 0, C.byref(h)) == -2
-    newton = make_cfg(walker, solver="newton")
-    assert lib.tmjx_model_create(walker.blob, len(walker.blob), C.byref(newton), 0, C.byref(h)) == -4
+    unknown = make_cfg(walker)
+    unknown.solver = 7
+    assert lib.tmjx_model_create(walker.blob, len(walker.blob), C.byref(unknown), 0, C.byref(h)) == -4
     g = Stepper(walker.blob, cfg, clips2, 8, 0)
     with pytest.raises(ValueError):
         g.step(torch.zeros(8, 3, device="cuda"))

@@ -574,7 +574,7 @@ __device__ void build_m(const Warp& w) {
   float* crb = w.at(m.o_cin);
   const float* cdof = w.at(m.o_cdof);
   float* L1 = w.at(m.o_big);
-  float* L2 = w.at(m.o_big + m.nMpad);
+  float* L2 = w.at(m.o_L2);
   float* f = L2;  // M-build scratch, dead before L2 is written
   sum_subtrees<10>(w, crb);
   for (int d = w.lane; d < m.nv; d += 32) {
@@ -596,6 +596,7 @@ __device__ void build_m(const Warp& w) {
   for (int e = w.lane; e < m.nM; e += 32) {
     const int i = m.m_row[e];
     L2[e] = (i == m.m_col[e]) ? L1[e] + m.dt * m.dof_damping[i] : L1[e];
+    if (m.o_L != m.o_big) w.at(m.o_L)[e] = L1[e];  // Newton: the raw inertia stays at o_big, its copy is factored
   }
   __syncwarp();
 }
@@ -628,7 +629,7 @@ __device__ void mul_m_raw(const Warp& w, const float* x, float out[kNvSlots]) {
 __device__ void factor_dual(const Warp& w) {
   const DevModel& m = w.m;
   const int lane = w.lane, i = lane & 15, hbit = lane & 16;
-  float* ps = w.at(m.o_big) + (hbit ? m.nMpad : 0) - i;  // entry (row r, column depth 16 j + i) of my matrix: ps[rowend(r) - 16 j]
+  float* ps = w.at(m.o_L) + (hbit ? m.nMpad : 0) - i;  // entry (row r, column depth 16 j + i) of my matrix: ps[rowend(r) - 16 j]
   for (int k = m.nv - 1; k >= 0; --k) {
     if ((k & 7) == 7) phase_sync();
     const int c = m.u_depth[k], re = m.u_rowend[k];
@@ -933,6 +934,92 @@ __device__ void make_constraint(const Warp& w, const float com[3], Rows& r, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------- Newton pieces
+// L^T D L of ONE sparse matrix in place (depth-lane mapping: lane d owns column depth d, d + 32 in the hi slot);
+// barrier-free for the same reason as factor_dual.  Used for the Newton Hessian, once per solver iteration.
+__device__ void factor_single(const Warp& w, float* L) {
+  const DevModel& m = w.m;
+  const int lane = w.lane;
+  float* pl = L - lane;
+  __syncwarp();
+  for (int k = m.nv - 1; k >= 0; --k) {
+    const int c = m.u_depth[k], re = m.u_rowend[k];
+    float* rk = pl + re;
+    const bool hi = c >= 32;
+    float l = 0.f, h = 0.f;
+    if (lane <= c) l = rk[0];
+    if (hi && lane + 32 <= c) h = rk[-32];
+    const float d = __shfl_sync(FULLMASK, hi ? h : l, c & 31);
+    const float inv = 1.f / d;
+    const float wl = l * inv, wh = h * inv;
+    if (lane < c) rk[0] = wl; else if (lane == c) rk[0] = inv;
+    if (hi) { if (lane + 32 < c) rk[-32] = wh; else if (lane + 32 == c) rk[-32] = inv; }
+    int ti = re - (c - 1);
+    for (int al = c - 1; al >= 0; --al, ++ti) {
+      float* t = pl + int(m.u_ancre[ti]);
+      const float a = __shfl_sync(FULLMASK, al >= 32 ? h : l, al & 31);
+      if (lane <= al) t[0] = fmaf(-a, wl, t[0]);
+      if (al >= 32 && lane + 32 <= al) t[-32] = fmaf(-a, wh, t[-32]);
+    }
+  }
+  __syncwarp();
+}
+
+// H = M + J^T diag(D * active) J in the sparse tree layout at o_L (solver.py Newton branch of update_gradient).
+// Limit rows add D to a diagonal entry; the four pyramid rows of an active contact are supported on the contact body's
+// root path, so J_r^T J_r only touches (dof, ancestor) pairs -- exactly the sparsity of M.  Depth-lane mapping: lane d
+// holds the row values of the chain dof at depth d; each chain row is one broadcast + LDS / 4 FMA / STS.
+__device__ void build_hessian(const Warp& w, const Rows& r, const float Jaref[kRowSlots]) {
+  const DevModel& m = w.m;
+  const int lane = w.lane;
+  float* H = w.at(m.o_L);
+  const float* M = w.at(m.o_big);
+  const float* cdof = w.at(m.o_cdof);
+  __syncwarp();
+  for (int e = lane; e < m.nM; e += 32) H[e] = M[e];
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < kLimSlots; ++q) {
+    const int l = lane + 32 * q;
+    if (l < m.nlimit && Jaref[4 + q] < 0.f && r.lsign[q] != 0.f) H[m.dof_madr[m.lim_dof[l]]] += r.D[4 + q];
+  }
+  __syncwarp();
+  // this lane's contact: D * active per pyramid row
+  float dk[4];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const bool on = r.cact && Jaref[k] < 0.f; dk[k] = on ? r.D[k] : 0.f; any |= on; }
+  unsigned todo = __ballot_sync(FULLMASK, any);
+  float* pl = H - lane;
+  while (todo) {
+    const int c = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float d0 = __shfl_sync(FULLMASK, dk[0], c), d1 = __shfl_sync(FULLMASK, dk[1], c), d2 = __shfl_sync(FULLMASK, dk[2], c),
+                d3 = __shfl_sync(FULLMASK, dk[3], c), mu = __shfl_sync(FULLMASK, r.mu, c);
+    const int cb = m.con_cb[c], e0 = m.cb_chain_start[cb], len = m.cb_chain_start[cb + 1] - e0;
+    const float* off = w.at(m.o_cin + m.c_off) + c * 3;
+    const float* t1 = w.at(m.o_cin + m.c_t1) + c * 3;
+    float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;  // the four row values at my chain dof
+    if (lane < len) {
+      const float* cd = cdof + m.cb_chain_dof[e0 + lane] * 6;
+      float vel[3], t2[3];
+      cross3(cd, off, vel);
+      vel[0] += cd[3]; vel[1] += cd[4]; vel[2] += cd[5];
+      cross3(m.plane_n, t1, t2);
+      const float jn = dot3(m.plane_n, vel), ja = dot3(t1, vel), jb = dot3(t2, vel);
+      j0 = jn + ja * mu; j1 = jn - ja * mu; j2 = jn + jb * mu; j3 = jn - jb * mu;
+    }
+    const float a0 = j0 * d0, a1 = j1 * d1, a2 = j2 * d2, a3 = j3 * d3;
+    for (int al = 0; al < len; ++al) {
+      const int re = m.u_rowend[m.cb_chain_dof[e0 + al]];
+      const float b0 = __shfl_sync(FULLMASK, a0, al), b1 = __shfl_sync(FULLMASK, a1, al), b2 = __shfl_sync(FULLMASK, a2, al),
+                  b3 = __shfl_sync(FULLMASK, a3, al);
+      if (lane <= al) pl[re] += b0 * j0 + b1 * j1 + b2 * j2 + b3 * j3;
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------- solver.solve (CG)
 struct LSPoint { float alpha, cost, d0, d1; };
 
@@ -974,7 +1061,8 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
                          const float Maw[kNvSlots], SolverOut& so) {
   const DevModel& m = w.m;
   float* sx = w.at(m.o_cin + m.c_sx);
-  const float* L1 = w.at(m.o_big);
+  const float* L1 = w.at(m.o_L);
+  const bool newton = m.solver == TMJX_SOLVER_NEWTON;
   float warm[kNvSlots];
   vget(w, w.at(m.o_warm), warm);
 
@@ -1027,6 +1115,10 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) grad[q] = Ma[q] - qfs[q] - qfc[q];
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) Mgrad[q] = grad[q];
+    if (newton) {  // H = M + J^T diag(D active) J, assembled and factored in the o_L block (same tree sparsity as M)
+      build_hessian(w, r, Jaref);
+      factor_single(w, w.at(m.o_L));
+    }
     solve_ld(w, L1, Mgrad);
   };
   // Context.create: cost = inf -> update_constraint sets prev_cost = inf, cost = c
@@ -1056,6 +1148,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     float jv[kRowSlots];
     vput(w, sx, search);
     __syncwarp();
+    if (newton) mul_m_raw(w, sx, mv);  // CG carries M*search by recurrence; Newton's direction has none
     apply_J(w, r, sx, jv);
     float qg[3];
     {
@@ -1127,6 +1220,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) { num += grad[q] * (Mgrad[q] - pMg[q]); den += pg[q] * pMg[q]; }
     float beta = wsum(num) / fmaxf(kMinVal, wsum(den));
     beta = fmaxf(0.f, beta);
+    if (newton) beta = 0.f;  // search = -H^-1 grad
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q] + beta * search[q]; mv[q] = -grad[q] + beta * mv[q]; }
     }
@@ -1159,11 +1253,11 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   float Maw[kNvSlots];
   mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  if (m.use_gen) { gen::factor_dual(w.at(m.o_big), w.lane); __syncwarp(); } else factor_dual(w);
+  if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane); __syncwarp(); } else factor_dual(w);
   phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
-  solve_ld(w, w.at(m.o_big), fo.qas);
+  solve_ld(w, w.at(m.o_L), fo.qas);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
   phase_sync();
@@ -1178,7 +1272,7 @@ __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   float qacc[kNvSlots];
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) qacc[q] = fo.qfs[q] + fo.so.qfc[q];
-  solve_ld(w, w.at(m.o_big + m.nMpad), qacc);
+  solve_ld(w, w.at(m.o_L2), qacc);
   float* qpos = w.at(m.o_qpos);
   float* qvel = w.at(m.o_qvel);
   float* act = w.at(m.o_act);
@@ -1646,22 +1740,25 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
   // 7 warps x 2 blocks = 14 resident envs per SM when the per-env slice allows it, else 4 warps x up to 3 blocks
-  // one block per SM, all of its 14 warps in lock-step (phase_sync); models whose per-env slice is too large for 14
-  // resident environments fall back to blocks of 4
-  m->envs_per_block = 14;
-  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { const int v = atoi(e); m->envs_per_block = v == 4 ? 4 : 14; }  // tuning knob
-  if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                                                  // tuning knob
+  // One block per SM with all of its warps in lock-step (phase_sync): 14 resident environments per SM when the per-env
+  // slice allows it (CG), 10 for larger slices (Newton keeps a third sparse matrix), else blocks of 4.
+  const size_t optin = prop.sharedMemPerBlockOptin;
+  m->envs_per_block = per_env * 14 <= optin ? 14 : (per_env * 10 <= optin ? 10 : 4);
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
+  if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
-  if (m->smem_per_block > prop.sharedMemPerBlockOptin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
-  m->max_blocks_per_sm = m->envs_per_block == 14 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
-  CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 4)));
-  if (per_env * 14 <= prop.sharedMemPerBlockOptin) {
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_env * 14)));
-  } else if (m->envs_per_block == 14) {
-    m->envs_per_block = 4; m->smem_per_block = per_env * 4;
-    m->max_blocks_per_sm = int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
+  if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
+  m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
+  const int dyn = int(m->smem_per_block);
+  if (m->envs_per_block == 14) {
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  } else if (m->envs_per_block == 10) {
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  } else {
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   }
   *out = m;
   return TMJX_OK;
@@ -1747,7 +1844,8 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   const int epb = m->envs_per_block;
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
-  if (epb == 14) tmjx_env_kernel<kStep, 14, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  if (epb == 10) tmjx_env_kernel<kStep, 10, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
+  else if (epb == 14) tmjx_env_kernel<kStep, 14, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   else tmjx_env_kernel<kStep, 4, 3><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
   CU(cudaGetLastError());
   return TMJX_OK;

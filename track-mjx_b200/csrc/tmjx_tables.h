@@ -98,8 +98,11 @@ struct DevModel {
   int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_cdof, o_cin, o_big, smem_floats;
   // phase A members of o_big
   int a_xipos, a_anchor, a_axis, a_cvel, a_cdofdot, a_cacc, a_force;
-  // phase B members: L1 at o_big, L2 at o_big + nMpad; f (M build) aliases L2
-  int nMpad;
+  // phase B members (sparse rows, nMpad floats each): raw inertia M at o_big; factor of M at o_L; factor of
+  // M + dt*diag(damping) at o_L2 = o_L + nMpad.  CG: o_L = o_big (factored in place).  Newton keeps the raw M (it is
+  // re-used every iteration for H = M + J^T D J and M*search) and factors a copy: o_L = o_big + nMpad, which is also
+  // where H is assembled and factored.  f (M-build scratch) aliases the o_L2 block.
+  int nMpad, o_L, o_L2;
   // solver-phase scratch inside o_cin
   int c_sx, c_sy, c_sD, c_sV, c_sW, c_sWb, c_off, c_t1, c_lf, c_end;
 };
@@ -151,7 +154,7 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   m.meaninertia_scale = opt[7] * float(std::max(1, m.nv));
   m.n_frames = cfg.physics_steps_per_control_step; m.solver = cfg.solver; m.iterations = cfg.iterations;
   m.ls_iterations = cfg.ls_iterations;
-  if (m.solver != TMJX_SOLVER_CG) throw std::runtime_error("only the CG solver is built in this round");
+  if (m.solver != TMJX_SOLVER_CG && m.solver != TMJX_SOLVER_NEWTON) throw std::runtime_error("unknown solver (unsupported)");
   if (m.nv > 32 * kNvSlots) throw std::runtime_error("nv > 96 unsupported");
   if (m.ncon > kMaxCon) throw std::runtime_error("ncon > 32 unsupported");
   if (m.na != 0 && m.na != m.nu) throw std::runtime_error("na must be 0 or nu");
@@ -468,8 +471,14 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     m.a_xipos = tk(nbody * 3); m.a_anchor = tk(njnt * 3); m.a_axis = tk(njnt * 3); m.a_cvel = tk(nbody * 6);
     m.a_cdofdot = tk(nv * 6); m.a_cacc = tk(nbody * 6); m.a_force = tk(nu);
     if (pad4(nv * 6) > m.nMpad) throw std::runtime_error("M-build scratch does not fit");
-    o += std::max(a, 2 * m.nMpad);
+    const int nmat = m.solver == TMJX_SOLVER_NEWTON ? 3 : 2;
+    m.o_L = m.o_big + (nmat - 2) * m.nMpad;
+    m.o_L2 = m.o_L + m.nMpad;
+    o += std::max(a, nmat * m.nMpad);
   }
+  if (m.solver == TMJX_SOLVER_NEWTON)
+    for (int s = 0; s < m.ncb; ++s)
+      if (cb_chain_start[s + 1] - cb_chain_start[s] > 32) throw std::runtime_error("Newton: contact chains longer than 32 dofs unsupported");
   m.smem_floats = o;
 }
 
