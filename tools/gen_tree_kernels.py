@@ -339,7 +339,7 @@ def emit_cuda(t: Tree) -> str:
     w("}")
     w("// Both L^T D L factorisations (M at L, M + dt diag(damping) at L + kNMpad), stacked half-warp per matrix; see")
     w("// factor_dual in tmjx_step.cu for the loop form of the same schedule (used for other trees).")
-    w("__device__ __noinline__ void factor_dual(float* __restrict__ L, int lane) {")
+    w("__device__ __noinline__ void factor_dual(float* __restrict__ L, int lane, bool sync) {")
     w("  const unsigned lb = 1u << lane;")
     w("  const int hbit = lane & 16;")
     w("  float* ps = L + (hbit ? kNMpad : 0) - (lane & 15);")
@@ -348,7 +348,7 @@ def emit_cuda(t: Tree) -> str:
     declared = set()
     for op in fir:
         if op[0] == "sync":
-            w("  __syncthreads();")
+            w("  if (sync) __syncthreads();")
         elif op[0] == "ld":
             _, r, imm, mask = op
             decl = "" if r in declared else "float "

@@ -130,6 +130,8 @@ __device__ __forceinline__ float impedance(const float* par, float pos) {
 // the 32 KB L1.5 instruction cache and the model-table lines in L1 are fetched once per block instead of once per
 // warp (ncu: `stall_no_inst` was the top stall reason with free-running warps).  Barriers sit only in block-uniform
 // control flow; environment-dependent loops (CG termination, line search) are masked, never broken out of.
+// DevModel.sync_level selects how many of the barrier sites are live (0: the one at the top of every substep, which
+// measured fastest; 1: major phases; 2: all).
 __device__ __forceinline__ void phase_sync() { __syncthreads(); }
 
 // ---------------------------------------------------------------------------------------------- per-warp context
@@ -446,7 +448,7 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
   }
   __syncwarp();
   scan_ancestors<6>(w, cvel);
-  phase_sync();
+  if (m.sync_level > 1) phase_sync();
   // cdof_dot per dof
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) {
@@ -489,7 +491,7 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
   }
   __syncwarp();
   scan_ancestors<6>(w, cacc);
-  phase_sync();
+  if (m.sync_level > 1) phase_sync();
   // local cfrc (in place of cacc)
 #pragma unroll
   for (int s = 0; s < kBodySlots; ++s) {
@@ -1135,7 +1137,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   const int max_iter = m.iterations != 1 ? m.iterations : 1;
   bool active = true;
   for (int iter = 0; iter < max_iter; ++iter) {
-    phase_sync();
+    if (m.sync_level > 0) phase_sync();
     if (active && m.iterations != 1) {
       const float improvement = (prev_cost - cost) / scale;
       const float gradient = sqrtf(vdot(grad, grad)) / scale;
@@ -1207,7 +1209,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
       for (int k = 0; k < kRowSlots; ++k) Jaref[k] += jv[k] * alpha;
     }
     }
-    phase_sync();
+    if (m.sync_level > 1) phase_sync();
     if (active) {
     // ---- body: update + Polak-Ribiere
     float pg[kNvSlots], pMg[kNvSlots];
@@ -1241,26 +1243,26 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   const DevModel& m = w.m;
   phase_sync();
   kinematics(w);
-  phase_sync();
+  if (m.sync_level > 1) phase_sync();
   com_pos(w, fo.com);
-  phase_sync();
+  if (m.sync_level > 1) phase_sync();
   com_vel_rne(w, fo.bias);
-  phase_sync();
+  if (m.sync_level > 0) phase_sync();
   passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
   __syncwarp();
   build_m(w);
-  phase_sync();
+  if (m.sync_level > 0) phase_sync();
   float Maw[kNvSlots];
   mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
   __syncwarp();
-  if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane); __syncwarp(); } else factor_dual(w);
-  phase_sync();
+  if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1); __syncwarp(); } else factor_dual(w);
+  if (m.sync_level > 0) phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
   solve_ld(w, w.at(m.o_L), fo.qas);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
-  phase_sync();
+  if (m.sync_level > 0) phase_sync();
   solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
   vput(w, w.at(m.o_warm), fo.so.qacc);
   __syncwarp();
@@ -1746,6 +1748,8 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->envs_per_block = per_env * 14 <= optin ? 14 : (per_env * 10 <= optin ? 10 : 4);
   if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
+  m->dm.sync_level = 0;  // measured: one barrier per substep keeps the block in lock-step; more only add skew
+  if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
