@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -148,6 +148,9 @@ def run_ours(args, rank, world, local_rank):
     shard = Shard(rank, world, ENVS_PER_GPU * world)   # weak scaling: 4096 envs per GPU, contiguous global env ids per rank
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
