@@ -58,5 +58,15 @@ def test_generated_factor_random_trees():
         _check_factor(G.Tree(parent), nv)
 
 
+def test_generated_mul_m_matches_dense():
+    rng = np.random.default_rng(3)
+    for tree in (G.rodent_tree(), G.Tree([-1] + [int(rng.integers(max(0, i - 4), i)) for i in range(1, 50)])):
+        M = G.random_tree_spd(tree, rng)
+        x = rng.normal(size=tree.nv)
+        y = G.run_mulm_ir(G.build_mulm_ir(tree), tree, G.sparse_from_dense(tree, M), x.astype(np.float32))
+        ref = M @ x
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-5
+
+
 def test_committed_header_is_current():
     assert open(G.OUT).read() == G.emit_cuda(G.rodent_tree())

@@ -209,6 +209,54 @@ def run_factor_ir(ir, t: Tree, M1: np.ndarray, M2: np.ndarray):
     return mem[pad:pad + t.nM].copy(), mem[pad + off2:pad + off2 + t.nM].copy()
 
 
+def build_mulm_ir(t: Tree):
+    """y = M x with the RAW sparse symmetric inertia (row i = dof i and its ancestors), x and y in dof-lane registers:
+    pivot p's value travels by one shuffle; its descendants use M[i][p] (their own row), its ancestors M[p][j] (row p)."""
+    nslot = (t.nv + 31) // 32
+    ir = []
+    for s in range(nslot):
+        ir.append(("mulset_lds", f"y{s}", f"x{s}", f"G{s}", 0, lane_mask(range(t.nv), s)))
+    for p in range(t.nv):
+        if not t.desc[p] and not t.anc[p]:
+            continue
+        ir.append(("shfl", "p", f"x{p // 32}", p % 32))
+        for s in range(nslot):
+            m = lane_mask(t.desc[p], s)
+            if m:
+                ir.append(("fma_lds", f"y{s}", f"D{s}", -t.depth[p], "p", m))
+            m = lane_mask(t.anc[p], s)
+            if m:
+                ir.append(("fma_lds", f"y{s}", f"U{s}", t.rowend[p], "p", m))
+    return ir
+
+
+def run_mulm_ir(ir, t: Tree, Ms: np.ndarray, x: np.ndarray) -> np.ndarray:
+    nslot = (t.nv + 31) // 32
+    pad = 64
+    Lp = np.concatenate([np.full(pad, np.nan, np.float32), Ms.astype(np.float32), np.full(pad, np.nan, np.float32)])
+    tabs = lane_tables(t)
+    regs = {}
+    for s in range(nslot):
+        v = np.zeros(32, np.float32)
+        n = min(32, t.nv - 32 * s)
+        v[:n] = x[32 * s:32 * s + n]
+        regs[f"x{s}"] = v
+        regs[f"y{s}"] = np.zeros(32, np.float32)
+    lanes = np.arange(32)
+    for op in ir:
+        if op[0] == "shfl":
+            regs[op[1]] = np.full(32, regs[op[2]][op[3]], np.float32)
+        elif op[0] == "mulset_lds":
+            _, yr, xr, ptr, imm, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            regs[yr] = np.where(act, (regs[xr] * Lp[pad + tabs[ptr] + imm]).astype(np.float32), np.float32(0))
+        elif op[0] == "fma_lds":
+            _, yr, ptr, imm, p, mask = op
+            act = ((mask >> lanes) & 1).astype(bool)
+            regs[yr] = np.where(act, (regs[yr] + Lp[pad + tabs[ptr] + imm] * regs[p]).astype(np.float32), regs[yr])
+    return np.concatenate([regs[f"y{s}"] for s in range(nslot)])[: t.nv]
+
+
 def lane_tables(t: Tree):
     nslot = (t.nv + 31) // 32
     tabs = {}
@@ -335,6 +383,29 @@ def emit_cuda(t: Tree) -> str:
             guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
             w(f"  {guard}{xr} *= {ptr}[{imm}];")
     w("  V3 r; r.a = x0; r.b = x1; r.c = x2;")
+    w("  return r;")
+    w("}")
+    w("// y = M x with the raw sparse inertia at M (before it is factored); x, y: dof-lane registers.")
+    w("__device__ __noinline__ V3 mul_m(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
+    w("  const float x0 = xin.a, x1 = xin.b, x2 = xin.c;")
+    w("  float y0 = 0.f, y1 = 0.f, y2 = 0.f, p;")
+    w("  const unsigned lb = 1u << lane;")
+    for s in range(3):
+        w(f"  const float* U{s} = L - dep{s};")
+        w(f"  const float* D{s} = L + rend{s};")
+        w(f"  const float* G{s} = L + (rend{s} - dep{s});")
+    for op in build_mulm_ir(t):
+        if op[0] == "shfl":
+            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]});")
+        elif op[0] == "mulset_lds":
+            _, yr, xr, ptr, imm, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}{yr} = {xr} * {ptr}[{imm}];")
+        elif op[0] == "fma_lds":
+            _, yr, ptr, imm, p, mask = op
+            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
+            w(f"  {guard}{yr} = fmaf({ptr}[{imm}], p, {yr});")
+    w("  V3 r; r.a = y0; r.b = y1; r.c = y2;")
     w("  return r;")
     w("}")
     w("// Both L^T D L factorisations (M at L, M + dt diag(damping) at L + kNMpad), stacked half-warp per matrix; see")

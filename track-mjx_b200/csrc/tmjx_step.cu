@@ -42,6 +42,37 @@ __device__ __forceinline__ float wsum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
   return v;
 }
+// Sum 9 values over the warp, all lanes get all totals, with 22 shuffles instead of 45: eight of the values are
+// reduced by recursive halving (offsets 16, 8, 4: a lane keeps one half of its list and sends the other, so after three
+// exchanges it owns ONE partial value), two butterflies finish that value, eight immediate-lane shuffles gather the
+// totals; the ninth value takes the plain butterfly.  The shared-memory / shuffle pipe is the scarce unit of this kernel.
+__device__ __forceinline__ void wsum9(float (&v)[9], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float y[4], z[2], w;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b4 ? v[2 * i] : v[2 * i + 1], keep = b4 ? v[2 * i + 1] : v[2 * i];
+    y[i] = keep + __shfl_xor_sync(FULLMASK, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? y[2 * i] : y[2 * i + 1], keep = b3 ? y[2 * i + 1] : y[2 * i];
+    z[i] = keep + __shfl_xor_sync(FULLMASK, send, 8);
+  }
+  {
+    const float send = b2 ? z[0] : z[1], keep = b2 ? z[1] : z[0];
+    w = keep + __shfl_xor_sync(FULLMASK, send, 4);
+  }
+  w += __shfl_xor_sync(FULLMASK, w, 2);
+  w += __shfl_xor_sync(FULLMASK, w, 1);
+  float t = v[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULLMASK, t, o);
+  v[8] = t;
+  // value i ended up in the lanes with 4*b2 + 2*b3 + b4 == i
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(FULLMASK, w, ((i >> 2) & 1) * 4 + ((i >> 1) & 1) * 8 + (i & 1) * 16);
+}
 __device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
   const float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -1039,14 +1070,21 @@ __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float J
       a0[p] += act ? q0[k] : 0.f; a1[p] += act ? q1[k] : 0.f; a2[p] += act ? q2[k] : 0.f;
     }
   }
+  if constexpr (N == 3) {
+    float v[9] = {a0[0], a1[0], a2[0], a0[1], a1[1], a2[1], a0[2], a1[2], a2[2]};
+    wsum9(v, int(threadIdx.x) & 31);
 #pragma unroll
-  for (int o = 16; o; o >>= 1)
+    for (int p = 0; p < N; ++p) { a0[p] = v[3 * p]; a1[p] = v[3 * p + 1]; a2[p] = v[3 * p + 2]; }
+  } else {
 #pragma unroll
-    for (int p = 0; p < N; ++p) {
-      a0[p] += __shfl_xor_sync(FULLMASK, a0[p], o);
-      a1[p] += __shfl_xor_sync(FULLMASK, a1[p], o);
-      a2[p] += __shfl_xor_sync(FULLMASK, a2[p], o);
-    }
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int p = 0; p < N; ++p) {
+        a0[p] += __shfl_xor_sync(FULLMASK, a0[p], o);
+        a1[p] += __shfl_xor_sync(FULLMASK, a1[p], o);
+        a2[p] += __shfl_xor_sync(FULLMASK, a2[p], o);
+      }
+  }
 #pragma unroll
   for (int p = 0; p < N; ++p) {
     const float t0 = a0[p] + qg[0], t1 = a1[p] + qg[1], t2 = a2[p] + qg[2], a = alpha[p];
@@ -1150,7 +1188,16 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     float jv[kRowSlots];
     vput(w, sx, search);
     __syncwarp();
-    if (newton) mul_m_raw(w, sx, mv);  // CG carries M*search by recurrence; Newton's direction has none
+    if (newton) {  // CG carries M*search by recurrence; Newton's direction has none
+      if (m.use_gen) {
+        gen::V3 v;
+        v.a = search[0]; v.b = search[1]; v.c = search[2];
+        v = gen::mul_m(w.at(m.o_big), v, w.lane, w.dep[0], w.dep[1], w.dep[2], w.rend[0], w.rend[1], w.rend[2]);
+        mv[0] = v.a; mv[1] = v.b; mv[2] = v.c;
+      } else {
+        mul_m_raw(w, sx, mv);
+      }
+    }
     apply_J(w, r, sx, jv);
     float qg[3];
     {
@@ -1252,8 +1299,17 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   __syncwarp();
   build_m(w);
   if (m.sync_level > 0) phase_sync();
-  float Maw[kNvSlots];
-  mul_m_raw(w, w.at(m.o_warm), Maw);   // M qacc_warmstart, while L1 still holds the raw inertia
+  float Maw[kNvSlots];   // M qacc_warmstart, while o_big still holds the raw inertia
+  if (m.use_gen) {
+    float wv[kNvSlots];
+    vget(w, w.at(m.o_warm), wv);
+    gen::V3 v;
+    v.a = wv[0]; v.b = wv[1]; v.c = wv[2];
+    v = gen::mul_m(w.at(m.o_big), v, w.lane, w.dep[0], w.dep[1], w.dep[2], w.rend[0], w.rend[1], w.rend[2]);
+    Maw[0] = v.a; Maw[1] = v.b; Maw[2] = v.c;
+  } else {
+    mul_m_raw(w, w.at(m.o_warm), Maw);
+  }
   __syncwarp();
   if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1); __syncwarp(); } else factor_dual(w);
   if (m.sync_level > 0) phase_sync();
