@@ -236,27 +236,38 @@ __device__ __forceinline__ void scan_ancestors(const Warp& w, float* buf) {
   }
 }
 
-// subtree sums: buf[b] <- sum of buf[c] over the subtree rooted at b (b >= 1), by doubling over descendant distance
+// subtree sums: buf[b] <- sum of buf[c] over the subtree rooted at b (b >= 1), by doubling over descendant distance.
+// The per-(round, body) descriptors are fetched up front (independent loads) so that the rounds only touch shared memory.
+constexpr int kMaxRounds = 6;  // trees up to 64 levels deep
 template <int NC>
 __device__ __forceinline__ void sum_subtrees(const Warp& w, float* buf) {
   const DevModel& m = w.m;
   float acc[kBodySlots][NC];
+  uint32_t pack[kBodySlots][kMaxRounds];
 #pragma unroll
   for (int s = 0; s < kBodySlots; ++s) {
     const int b = w.lane + 32 * s;
 #pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) pack[s][r] = (b < m.nbody && r < m.nround) ? m.dsc_pack[r * m.nbody + b] : 0u;
+#pragma unroll
     for (int k = 0; k < NC; ++k) acc[s][k] = b < m.nbody ? buf[b * NC + k] : 0.f;
   }
-  for (int r = 0; r < m.nround; ++r) {
+#pragma unroll
+  for (int r = 0; r < kMaxRounds; ++r) {
+    if (r >= m.nround) break;
     bool on[kBodySlots];
 #pragma unroll
     for (int s = 0; s < kBodySlots; ++s) {
-      const int b = w.lane + 32 * s;
-      on[s] = false;
-      if (b < m.nbody) {
-        const int e0 = m.dsc_start[r * (m.nbody + 1) + b], e1 = m.dsc_start[r * (m.nbody + 1) + b + 1];
-        on[s] = e1 > e0;
-        for (int e = e0; e < e1; ++e) {
+      const uint32_t p = pack[s][r];
+      const int cnt = int(p >> 16);
+      on[s] = cnt != 0;
+      if (cnt == 1) {
+        const float* src = buf + int(p & 0xffffu) * NC;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc[s][k] += src[k];
+      } else if (cnt > 1) {
+        const int e0 = int(p & 0xffffu);
+        for (int e = e0; e < e0 + cnt; ++e) {
           const float* src = buf + int(m.dsc_list[e]) * NC;
 #pragma unroll
           for (int k = 0; k < NC; ++k) acc[s][k] += src[k];
@@ -617,19 +628,34 @@ __device__ void build_m(const Warp& w) {
     for (int k = 0; k < 6; ++k) f[d * 6 + k] = t[k];
   }
   __syncwarp();
-  for (int e = w.lane; e < m.nM; e += 32) {
-    const int i = m.m_row[e], j = m.m_col[e];
-    float v = 0.f;
+  __syncwarp();  // f (aliasing the o_L2 block) is complete
+  // both matrices (and Newton's copy) from one pass; the entry values are kept in registers across the barrier that
+  // retires the scratch f
+  {
+    constexpr int kMaxIt = 40;  // nM <= 1280
+    float v[kMaxIt];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) v += f[i * 6 + k] * cdof[j * 6 + k];
-    if (i == j) v += m.dof_armature[i];
-    L1[e] = v;
-  }
-  __syncwarp();  // f (aliasing L2) is dead from here
-  for (int e = w.lane; e < m.nM; e += 32) {
-    const int i = m.m_row[e];
-    L2[e] = (i == m.m_col[e]) ? L1[e] + m.dt * m.dof_damping[i] : L1[e];
-    if (m.o_L != m.o_big) w.at(m.o_L)[e] = L1[e];  // Newton: the raw inertia stays at o_big, its copy is factored
+    for (int it = 0; it < kMaxIt; ++it) {
+      const int e = w.lane + 32 * it;
+      v[it] = 0.f;
+      if (e < m.nM) {
+        const int rc = m.m_rc[e], i = rc & 0xff, j = rc >> 8;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a += f[i * 6 + k] * cdof[j * 6 + k];
+        v[it] = a + m.m_add1[e];
+      }
+    }
+    __syncwarp();  // f is dead from here
+#pragma unroll
+    for (int it = 0; it < kMaxIt; ++it) {
+      const int e = w.lane + 32 * it;
+      if (e < m.nM) {
+        L1[e] = v[it];
+        L2[e] = v[it] + m.m_add2[e];
+        if (m.o_L != m.o_big) w.at(m.o_L)[e] = v[it];  // Newton: the raw inertia stays at o_big, its copy is factored
+      }
+    }
   }
   __syncwarp();
 }

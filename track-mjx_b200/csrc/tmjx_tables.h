@@ -50,6 +50,12 @@ struct DevModel {
   int nround;
   const uint8_t *anc_pow, *dsc_list;
   const uint16_t* dsc_start;
+  /* dsc_pack[r * nbody + b] = count << 16 | (count == 1 ? the descendant : first index into dsc_list): one load per
+   * (round, body) on the common path (chains: at most one descendant at each distance) */
+  const uint32_t* dsc_pack;
+  /* per sparse-inertia entry: row | col << 8, and the two diagonal additions (armature; armature + dt * damping) */
+  const uint16_t* m_rc;
+  const float *m_add1, *m_add2;
   // ---- per joint
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_body;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_qpos0, *jnt_springref;
@@ -206,6 +212,12 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
         if (depth[c] - depth[i] == (1 << r) && anc_pow[size_t(r) * nbody + c] == i) dsc_list.push_back(uint8_t(c));
     }
   }
+  std::vector<int32_t> dsc_pack(size_t(std::max(nround, 1)) * nbody, 0);
+  for (int r = 0; r < nround; ++r)
+    for (int i = 0; i < nbody; ++i) {
+      const int e0 = dsc_start[size_t(r) * (nbody + 1) + i], e1 = dsc_start[size_t(r) * (nbody + 1) + i + 1], cnt = e1 - e0;
+      dsc_pack[size_t(r) * nbody + i] = int32_t((uint32_t(cnt) << 16) | uint32_t(cnt == 1 ? dsc_list[e0] : e0));
+    }
   if (dsc_start.empty()) dsc_start.push_back(0);
   if (dsc_list.empty()) dsc_list.push_back(0);
   if (nbody > 255) throw std::runtime_error("more than 255 bodies unsupported");
@@ -429,6 +441,18 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   PI(dof_qadr, dof_qadr);
   PF(dof_armature, b.f32("dof_armature")); PF(dof_damping, b.f32("dof_damping"));
   P8(anc_pow, anc_pow); P8(dsc_list, dsc_list);
+  m.dsc_pack = TMJX_OFF(uint32_t, push(t.i32, dsc_pack));
+  {
+    auto arm = b.f32("dof_armature"), damp = b.f32("dof_damping");
+    std::vector<uint16_t> rc(m.nM);
+    std::vector<float> add1(m.nM, 0.f), add2(m.nM, 0.f);
+    for (int e = 0; e < m.nM; ++e) {
+      rc[e] = uint16_t(m_row[e] | (m_col[e] << 8));
+      if (m_row[e] == m_col[e]) { add1[e] = arm[m_row[e]]; add2[e] = m.dt * damp[m_row[e]]; }
+    }
+    m.m_rc = TMJX_OFF(uint16_t, push(t.u16, rc));
+    PF(m_add1, add1); PF(m_add2, add2);
+  }
   m.dsc_start = TMJX_OFF(uint16_t, push(t.u16, dsc_start));
   P8(m_anc, m_anc); P8(m_row, m_row); P8(m_col, m_col); P8(tri_a, tri_a); P8(tri_b, tri_b);
   m.dmask = TMJX_OFF(uint32_t, push(t.i32, dmask)); m.amask = TMJX_OFF(uint32_t, push(t.i32, amask));
@@ -496,6 +520,9 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   RI(dof_body); RI(dof_jnt); RI(dof_madr); RI(dof_depth); RI(dof_limit); RI(dof_qadr);
   RF(dof_armature); RF(dof_damping);
   R8(anc_pow); R8(dsc_list);
+  m.dsc_pack = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dsc_pack);
+  m.m_rc = d16 + reinterpret_cast<uintptr_t>(m.m_rc);
+  RF(m_add1); RF(m_add2);
   m.dsc_start = d16 + reinterpret_cast<uintptr_t>(m.dsc_start);
   R8(m_anc); R8(m_row); R8(m_col); R8(tri_a); R8(tri_b);
   m.dmask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dmask);
