@@ -18,7 +18,7 @@ cat $OUT/${TAG}_bench.json | cut -c1-600
 if [ -z "$2" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:tmjx_env_kernelILb1 -s 4 -c 1 -f -o $OUT/${TAG}_prof \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:tmjx_env_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
   ls -la $OUT/${TAG}_prof.ncu-rep
 fi
