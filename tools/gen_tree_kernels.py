@@ -113,6 +113,7 @@ def build_solve_ir(t: Tree):
 #   ("sync",)                       block phase barrier (instruction-cache lock-step)
 def half_mask(n):
     """lanes i < n of both half-warps (n in 0..16)."""
+    # (the row updates of the factorisation run unmasked, see build_factor_ir)
     n = max(0, min(16, n))
     m16 = (1 << n) - 1
     return m16 | (m16 << 16)
@@ -165,7 +166,10 @@ def build_factor_ir(t: Tree):
                 row = chain[c - al]
                 ir.append(("shflh", "a", f"r{k}_{al >> 4}", al & 15))
                 for j in range(al // 16 + 1):
-                    ir.append(("fnma_reg", f"r{row}_{j}", "a", f"w{j}", half_mask(al - 16 * j + 1)))
+                    # UNMASKED: lanes beyond the row's last column (i > al - 16 j) get polluted, but a lane's entry is only
+                    # ever combined with the same lane of other rows, shuffles read lanes <= depth and stores are masked,
+                    # so the pollution never reaches a valid entry (run_factor_ir executes it on all 32 lanes, too)
+                    ir.append(("fnma_reg", f"r{row}_{j}", "a", f"w{j}", 0xFFFFFFFF))
         for r in t.anc[bottom]:                       # ancestors of the chain: updated, not yet eliminated
             for j in range(t.depth[r] // 16 + 1):
                 ir.append(("st", t.rowend[r] - 16 * j, f"r{r}_{j}", half_mask(t.depth[r] - 16 * j + 1)))
@@ -203,7 +207,8 @@ def run_factor_ir(ir, t: Tree, M1: np.ndarray, M2: np.ndarray):
         elif op[0] == "fnma_reg":
             _, dst, a, w, mask = op
             act = ((mask >> lanes) & 1).astype(bool)
-            regs[dst] = np.where(act, (regs[dst] - regs[a] * regs[w]).astype(np.float32), regs[dst])
+            with np.errstate(all="ignore"):
+                regs[dst] = np.where(act, (regs[dst] - regs[a] * regs[w]).astype(np.float32), regs[dst])
         else:
             raise ValueError(op)
     return mem[pad:pad + t.nM].copy(), mem[pad + off2:pad + off2 + t.nM].copy()
@@ -343,6 +348,23 @@ def random_tree_spd(t: Tree, rng) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------ CUDA printer
+
+def _pred_fma(xr, ptr, imm, preg, mask, neg):
+    """One predicated LDS + FFMA in place (inline PTX).  The C form `if (lb & m) x = fmaf(..)` compiled to a predicated FFMA
+    into a temporary plus a predicated MOV and spilled predicates into a GPR bit-mask (ncu: 16 % IMAD.MOV/MOV, 12 % LOP3 of
+    the solve's instructions); this pins it to LOP3(pred) + LDS + FFMA."""
+    full = 0xFFFFFFFF
+    sign = ""
+    if neg:
+        preg = "n" + preg   # the negated pivot value (one FADD per pivot instead of one operand negation per use)
+    if mask == full:
+        return (f'  asm("{{.reg .f32 t; ld.shared.f32 t, [%2+{4 * imm}]; {sign}fma.rn.f32 %0, t, %1, %0;}}" '
+                f': "+f"({xr}) : "f"({preg}), "r"({ptr}));')
+    return (f'  asm("{{.reg .pred q; .reg .b32 m; .reg .f32 t; and.b32 m, %3, 0x{mask:08x}; setp.ne.u32 q, m, 0; '
+            f'ld.shared.f32 t, [%2+{4 * imm}]; {sign}@q fma.rn.f32 %0, t, %1, %0;}}" '
+            f': "+f"({xr}) : "f"({preg}), "r"({ptr}), "r"(lb));')
+
+
 def emit_cuda(t: Tree) -> str:
     ir = build_solve_ir(t)
     nslot = (t.nv + 31) // 32
@@ -363,21 +385,21 @@ def emit_cuda(t: Tree) -> str:
     w("#ifdef __CUDACC__")
     w("// x <- (L^T D L)^-1 x.  L: this env's sparse factor in shared memory (diagonal holds 1/D);")
     w("// dep* / rend* : depth and row-end of the dofs this lane owns (lane, lane+32, lane+64).")
-    w("__device__ __noinline__ V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
-    w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c, p;")
+    w("static __device__ __noinline__ V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
+    w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c, p, np;")
     w("  const unsigned lb = 1u << lane;")
+    w("  const unsigned sL = static_cast<unsigned>(__cvta_generic_to_shared(L));")
     for s in range(3):
-        w(f"  const float* U{s} = L - dep{s};")
-        w(f"  const float* D{s} = L + rend{s};")
+        w(f"  const unsigned U{s} = sL - 4u * unsigned(dep{s});")
+        w(f"  const unsigned D{s} = sL + 4u * unsigned(rend{s});")
         w(f"  const float* G{s} = L + (rend{s} - dep{s});")
     full = 0xFFFFFFFF
     for op in ir:
         if op[0] == "shfl":
-            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]});")
+            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]}); np = -p;")
         elif op[0] == "fnma_lds":
             _, xr, ptr, imm, p, mask = op
-            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
-            w(f"  {guard}{xr} = fmaf(-{ptr}[{imm}], p, {xr});")
+            w(_pred_fma(xr, ptr, imm, "p", mask, True))
         elif op[0] == "mul_lds":
             _, xr, ptr, imm, mask = op
             guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
@@ -386,13 +408,14 @@ def emit_cuda(t: Tree) -> str:
     w("  return r;")
     w("}")
     w("// y = M x with the raw sparse inertia at M (before it is factored); x, y: dof-lane registers.")
-    w("__device__ __noinline__ V3 mul_m(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
+    w("static __device__ __noinline__ V3 mul_m(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
     w("  const float x0 = xin.a, x1 = xin.b, x2 = xin.c;")
     w("  float y0 = 0.f, y1 = 0.f, y2 = 0.f, p;")
     w("  const unsigned lb = 1u << lane;")
+    w("  const unsigned sL = static_cast<unsigned>(__cvta_generic_to_shared(L));")
     for s in range(3):
-        w(f"  const float* U{s} = L - dep{s};")
-        w(f"  const float* D{s} = L + rend{s};")
+        w(f"  const unsigned U{s} = sL - 4u * unsigned(dep{s});")
+        w(f"  const unsigned D{s} = sL + 4u * unsigned(rend{s});")
         w(f"  const float* G{s} = L + (rend{s} - dep{s});")
     for op in build_mulm_ir(t):
         if op[0] == "shfl":
@@ -403,14 +426,13 @@ def emit_cuda(t: Tree) -> str:
             w(f"  {guard}{yr} = {xr} * {ptr}[{imm}];")
         elif op[0] == "fma_lds":
             _, yr, ptr, imm, p, mask = op
-            guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
-            w(f"  {guard}{yr} = fmaf({ptr}[{imm}], p, {yr});")
+            w(_pred_fma(yr, ptr, imm, "p", mask, False))
     w("  V3 r; r.a = y0; r.b = y1; r.c = y2;")
     w("  return r;")
     w("}")
     w("// Both L^T D L factorisations (M at L, M + dt diag(damping) at L + kNMpad), stacked half-warp per matrix; see")
     w("// factor_dual in tmjx_step.cu for the loop form of the same schedule (used for other trees).")
-    w("__device__ __noinline__ void factor_dual(float* __restrict__ L, int lane, bool sync) {")
+    w("static __device__ __noinline__ void factor_dual(float* __restrict__ L, int lane, bool sync) {")
     w("  const unsigned lb = 1u << lane;")
     w("  const int hbit = lane & 16;")
     w("  float* ps = L + (hbit ? kNMpad : 0) - (lane & 15);")

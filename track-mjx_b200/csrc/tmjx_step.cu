@@ -33,6 +33,20 @@
 
 namespace tmjx {
 
+struct KArgs {
+  DevModel m;
+  const DevTask* task;
+  const float* clips;
+  int n_clips, clip_len;
+  TmjxState st;
+  TmjxOut out;
+  const float* action;
+  int n_env;
+  unsigned flags;
+};
+
+#ifdef TMJX_VARIANT  // device code: compiled once per residency variant, in parallel (see __graft_entry__.build)
+namespace {      // internal linkage: every variant translation unit carries its own copy of the device functions
 #define FULLMASK 0xffffffffu
 constexpr float kMinVal = 1e-15f;
 
@@ -810,11 +824,38 @@ __device__ void apply_J(const Warp& w, const Rows& r, const float* x, float jv[k
   const DevModel& m = w.m;
   const float* cdof = w.at(m.o_cdof);
   float* sV = w.at(m.o_cin + m.c_sV);
-  for (int t = w.lane; t < m.ncb * 6; t += 32) {
-    const int cb = t / 6, k = t % 6;
-    float acc = 0.f;
-    for (int e = m.cb_chain_start[cb]; e < m.cb_chain_start[cb + 1]; ++e) { const int d = m.cb_chain_dof[e]; acc += cdof[d * 6 + k] * x[d]; }
-    sV[t] = acc;
+  if (m.use_seg) {
+    // segment partial sums, then each contact body adds the (<= 4) segments of its root path
+    float* sP = w.at(m.o_cin + m.c_sP);
+    const uint32_t st0 = m.seg_task[w.lane], st1 = m.seg_task[w.lane + 32], ct0 = m.cb_task[w.lane], ct1 = m.cb_task[w.lane + 32];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const uint32_t st = sl ? st1 : st0;
+      const int d0 = st & 0xff, len = (st >> 8) & 0xf, k = (st >> 12) & 7;
+      const float* cd = cdof + d0 * 6 + k;
+      const float* xs = x + d0;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i < len) acc = fmaf(cd[i * 6], xs[i], acc);
+      if (st & 0x8000u) sP[w.lane + 32 * sl] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const uint32_t ct = sl ? ct1 : ct0;
+      const int k = (ct >> 16) & 7;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int sg = (ct >> (4 * j)) & 0xf; if (sg != 0xf) acc += sP[sg * 6 + k]; }
+      if (ct & 0x80000u) sV[w.lane + 32 * sl] = acc;
+    }
+  } else {
+    for (int t = w.lane; t < m.ncb * 6; t += 32) {
+      const int cb = t / 6, k = t % 6;
+      float acc = 0.f;
+      for (int e = m.cb_chain_start[cb]; e < m.cb_chain_start[cb + 1]; ++e) { const int d = m.cb_chain_dof[e]; acc += cdof[d * 6 + k] * x[d]; }
+      sV[t] = acc;
+    }
   }
   __syncwarp();
   jv[0] = jv[1] = jv[2] = jv[3] = 0.f;
@@ -863,6 +904,53 @@ __device__ void apply_JT(const Warp& w, const Rows& r, const float f[kRowSlots],
     if (l < m.nlimit) lf[l] = r.lsign[q] * f[4 + q];
   }
   __syncwarp();
+  if (m.use_seg) {
+    // per contact body: sum of its contacts' wrenches; per segment: sum over the contact bodies below it; per dof: one
+    // 6-vector product with its segment's wrench
+    float* sP = w.at(m.o_cin + m.c_sP);
+    const uint32_t st0 = m.seg_task[w.lane], st1 = m.seg_task[w.lane + 32], ct0 = m.cb_task[w.lane], ct1 = m.cb_task[w.lane + 32];
+    const uint32_t ds3 = m.dof_seg3[w.lane];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const uint32_t ct = sl ? ct1 : ct0;
+      const int k = (ct >> 16) & 7, c0 = (ct >> 20) & 0xff, cn = ct >> 28;
+      const float* src = sW + c0 * 6 + k;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) if (i < cn) acc += src[i * 6];
+      for (int i = 6; i < cn; ++i) acc += src[i * 6];
+      if (ct & 0x80000u) sWb[w.lane + 32 * sl] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const uint32_t st = sl ? st1 : st0;
+      const int k = (st >> 12) & 7, b0 = (st >> 16) & 0xff, bn = (st >> 24) & 0xf;
+      const float* src = sWb + b0 * 6 + k;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i < bn) acc += src[i * 6];
+      for (int i = 8; i < bn; ++i) acc += src[i * 6];
+      if (st & 0x8000u) sP[w.lane + 32 * sl] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kNvSlots; ++q) {
+      const int d = w.lane + 32 * q;
+      const int sg = (ds3 >> (8 * q)) & 0xff;
+      float acc = 0.f;
+      if (sg != 0xff) {
+        const float* W = sP + sg * 6;
+        const float* cd = cdof + d * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fmaf(cd[k], W[k], acc);
+      }
+      if (d < m.nv) { const int l = m.dof_limit[d]; if (l >= 0) acc += lf[l]; }
+      out[q] = acc;
+    }
+    __syncwarp();
+    return;
+  }
   for (int t = w.lane; t < m.ncb * 6; t += 32) {
     const int cb = t / 6, k = t % 6;
     float acc = 0.f;
@@ -1092,8 +1180,8 @@ __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float J
     a0[p] = a1[p] = a2[p] = 0.f;
 #pragma unroll
     for (int k = 0; k < kRowSlots; ++k) {
-      const bool act = (Jaref[k] + alpha[p] * jv[k]) < 0.f;
-      a0[p] += act ? q0[k] : 0.f; a1[p] += act ? q1[k] : 0.f; a2[p] += act ? q2[k] : 0.f;
+      // three predicated FADDs (the select form compiled to FSEL + FADD pairs)
+      if ((Jaref[k] + alpha[p] * jv[k]) < 0.f) { a0[p] += q0[k]; a1[p] += q1[k]; a2[p] += q2[k]; }
     }
   }
   if constexpr (N == 3) {
@@ -1473,17 +1561,6 @@ __device__ void write_obs(const Warp& w, const DevTask& t, const float* __restri
   (void)bad;
 }
 
-struct KArgs {
-  DevModel m;
-  const DevTask* task;
-  const float* clips;
-  int n_clips, clip_len;
-  TmjxState st;
-  TmjxOut out;
-  const float* action;
-  int n_env;
-  unsigned flags;
-};
 
 // kWPB warps (= environments) per block; (4, 3) and (7, 2) are the two residency points that matter on B200:
 // 12 and 14 resident environments per SM (the latter needs <= 144 registers and fits 4096 envs in two waves of 148 SMs)
@@ -1747,6 +1824,56 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
   }
 }
 
+}  // namespace
+
+// per-variant entry points (one translation unit per residency variant; the C ABI below dispatches on envs_per_block)
+#if TMJX_VARIANT == 14
+#define TMJX_WPB 14
+#define TMJX_MINB 1
+#elif TMJX_VARIANT == 10
+#define TMJX_WPB 10
+#define TMJX_MINB 1
+#else
+#define TMJX_WPB 4
+#define TMJX_MINB 3
+#endif
+#define TMJX_CAT2(a, b) a##b
+#define TMJX_CAT(a, b) TMJX_CAT2(a, b)
+cudaError_t TMJX_CAT(variant_attr_, TMJX_VARIANT)(int dyn) {
+  cudaError_t e = cudaFuncSetAttribute(tmjx_env_kernel<true, TMJX_WPB, TMJX_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tmjx_env_kernel<false, TMJX_WPB, TMJX_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+}
+cudaError_t TMJX_CAT(variant_launch_, TMJX_VARIANT)(bool step, const KArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (step) tmjx_env_kernel<true, TMJX_WPB, TMJX_MINB><<<grid, TMJX_WPB * 32, smem, st>>>(a);
+  else tmjx_env_kernel<false, TMJX_WPB, TMJX_MINB><<<grid, TMJX_WPB * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+}  // namespace tmjx
+#else  // ------------------------------------------------------------------------------ main translation unit
+// a development build may carry a subset of the variants (TMJX_BUILD_VARIANTS); a missing one fails loudly
+#define TMJX_DECL_VARIANT(v) \
+  cudaError_t variant_attr_##v(int dyn); \
+  cudaError_t variant_launch_##v(bool step, const KArgs& a, int grid, size_t smem, cudaStream_t st);
+#define TMJX_STUB_VARIANT(v) \
+  static cudaError_t variant_attr_##v(int) { return cudaErrorNotSupported; } \
+  static cudaError_t variant_launch_##v(bool, const KArgs&, int, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+#ifdef TMJX_HAVE_VARIANT_14
+TMJX_DECL_VARIANT(14)
+#else
+TMJX_STUB_VARIANT(14)
+#endif
+#ifdef TMJX_HAVE_VARIANT_10
+TMJX_DECL_VARIANT(10)
+#else
+TMJX_STUB_VARIANT(10)
+#endif
+#ifdef TMJX_HAVE_VARIANT_4
+TMJX_DECL_VARIANT(4)
+#else
+TMJX_STUB_VARIANT(4)
+#endif
+
 // FP32 FMA-throughput microbenchmark (roofline denominator)
 __global__ void fma_peak_kernel(float* out, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -1830,22 +1957,14 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->envs_per_block = per_env * 14 <= optin ? 14 : (per_env * 10 <= optin ? 10 : 4);
   if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
+  if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
   m->dm.sync_level = 0;  // measured: one barrier per substep keeps the block in lock-step; more only add skew
   if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
   const int dyn = int(m->smem_per_block);
-  if (m->envs_per_block == 14) {
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  } else if (m->envs_per_block == 10) {
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  } else {
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<true, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU(cudaFuncSetAttribute(tmjx_env_kernel<false, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  }
+  CU(m->envs_per_block == 14 ? variant_attr_14(dyn) : (m->envs_per_block == 10 ? variant_attr_10(dyn) : variant_attr_4(dyn)));
   *out = m;
   return TMJX_OK;
 }
@@ -1930,10 +2049,9 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   const int epb = m->envs_per_block;
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
-  if (epb == 10) tmjx_env_kernel<kStep, 10, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
-  else if (epb == 14) tmjx_env_kernel<kStep, 14, 1><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
-  else tmjx_env_kernel<kStep, 4, 3><<<grid, epb * 32, m->smem_per_block, static_cast<cudaStream_t>(stream)>>>(a);
-  CU(cudaGetLastError());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(epb == 14 ? variant_launch_14(kStep, a, grid, m->smem_per_block, st)
+               : (epb == 10 ? variant_launch_10(kStep, a, grid, m->smem_per_block, st) : variant_launch_4(kStep, a, grid, m->smem_per_block, st)));
   return TMJX_OK;
 }
 
@@ -1983,3 +2101,4 @@ double tmjx_fp32_peak_tflops(int device, void* stream) {
 }
 
 }  // extern "C"
+#endif  // TMJX_VARIANT

@@ -11,6 +11,7 @@
 #ifndef TMJX_TABLES_H_
 #define TMJX_TABLES_H_
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -101,6 +102,16 @@ struct DevModel {
   const int *con_geom, *con_side /* +1 / -1 capsule end, 0 single */, *con_cb;
   const float* con_par;       /* [ncon, 12]: mu invweight k b dmin dmax width mid power includemargin pad pad */
   const int *cb_body, *cb_chain_start, *cb_chain_dof, *dof_cb_start, *dof_cb, *cb_con_start, *cb_con;
+  /* Contact-chain SEGMENTS (use_seg): the root paths of the contact bodies share long prefixes, so J x and J^T f are
+   * evaluated on the maximal runs of consecutive chain dofs with the same set of contact bodies below them (10 runs of
+   * <= 7 dofs for the rodent instead of 8 chains of 13..18).  Lane tasks t = lane + 32 * slot (two slots), packed words:
+   *   seg_task[t]: bits 0-7 first dof, 8-11 length, 12-14 k (spatial component), 15 valid, 16-23 first contact body of the
+   *                segment's subtree, 24-27 their count         (task = segment t / 6, component t % 6)
+   *   cb_task[t] : bits 0-15 four 4-bit segment ids of the body's root path (0xf = none), 16-18 k, 19 valid,
+   *                20-27 first contact of the body, 28-31 contact count   (task = contact body t / 6, component t % 6)
+   *   dof_seg3[lane]: segment id (0xff = none) of dofs lane, lane + 32, lane + 64 in bytes 0..2 */
+  int use_seg, nseg;
+  const uint32_t *seg_task, *cb_task, *dof_seg3;
   // ---- shared-memory layout (float offsets inside one environment's slice)
   int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_cdof, o_cin, o_big, smem_floats;
   // phase A members of o_big
@@ -111,7 +122,7 @@ struct DevModel {
   // where H is assembled and factored.  f (M-build scratch) aliases the o_L2 block.
   int nMpad, o_L, o_L2;
   // solver-phase scratch inside o_cin
-  int c_sx, c_sy, c_sD, c_sV, c_sW, c_sWb, c_off, c_t1, c_lf, c_end;
+  int c_sx, c_sy, c_sD, c_sV, c_sW, c_sWb, c_off, c_t1, c_lf, c_sP, c_end;
 };
 
 /* Task-layer constants + packed clip table. */
@@ -372,12 +383,10 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   const int plane_body = b.i32("plane_bodyid")[0];
   for (int k = 0; k < 3; ++k) { m.plane_pos[k] = plane[k]; m.plane_n[k] = plane[3 + k]; }
   std::vector<int32_t> cb_body, cg_cb(m.ncg);
-  for (int g = 0; g < m.ncg; ++g) {
-    int slot = -1;
-    for (size_t s = 0; s < cb_body.size(); ++s) if (cb_body[s] == cg_body[g]) slot = int(s);
-    if (slot < 0) { slot = int(cb_body.size()); cb_body.push_back(cg_body[g]); }
-    cg_cb[g] = slot;
-  }
+  for (int g = 0; g < m.ncg; ++g) cb_body.push_back(cg_body[g]);
+  std::sort(cb_body.begin(), cb_body.end());   // body ids are depth-first: a subtree's contact bodies are one range
+  cb_body.erase(std::unique(cb_body.begin(), cb_body.end()), cb_body.end());
+  for (int g = 0; g < m.ncg; ++g) cg_cb[g] = int(std::lower_bound(cb_body.begin(), cb_body.end(), cg_body[g]) - cb_body.begin());
   m.ncb = int(cb_body.size());
   std::vector<int32_t> con_geom, con_side, con_cb;
   std::vector<float> con_par;
@@ -419,6 +428,59 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     for (int s : dof_cb_l[d]) dof_cb.push_back(s);
   }
   dof_cb_start[nv] = int(dof_cb.size());
+  // ---- contact-chain segments
+  std::vector<int32_t> seg_task(64, 0), cb_task(64, 0), dof_seg3(32, 0x00ffffff);
+  m.use_seg = 0; m.nseg = 0;
+  {
+    std::vector<int> seg_d0, seg_len, seg_of(nv, -1), seg_cb0, seg_cbn;
+    bool ok = m.ncb * 6 <= 64 && m.ncb <= 32;
+    std::vector<uint32_t> cset(nv, 0);
+    if (ok) for (int d = 0; d < nv; ++d) for (int s2 : dof_cb_l[d]) cset[d] |= 1u << s2;
+    for (int d = 0; d < nv && ok; ++d) {
+      if (!cset[d]) continue;
+      const bool cont = d > 0 && dof_parentid[d] == d - 1 && cset[d - 1] == cset[d] && seg_len.back() < 8;
+      if (!cont) {
+        seg_d0.push_back(d); seg_len.push_back(0);
+        int lo = 0; while (!((cset[d] >> lo) & 1u)) ++lo;
+        int n = 0; while (lo + n < 32 && ((cset[d] >> (lo + n)) & 1u)) ++n;
+        if (cset[d] != (((n == 32 ? 0u : (1u << n)) - 1u) << lo)) ok = false;   // subtree bodies must be one range
+        if (n > 15) ok = false;
+        seg_cb0.push_back(lo); seg_cbn.push_back(n);
+      }
+      ++seg_len.back();
+      seg_of[d] = int(seg_d0.size()) - 1;
+    }
+    const int nseg = int(seg_d0.size());
+    if (nseg * 6 > 64 || nseg > 15 || nv > 96) ok = false;
+    for (int s2 = 0; s2 < m.ncb && ok; ++s2) {
+      // root path of the body in segments, contact range of the body
+      std::vector<int> path;
+      for (int e = cb_chain_start[s2 + 1] - 1; e >= cb_chain_start[s2]; --e) {
+        const int sg = seg_of[cb_chain_dof[e]];
+        if (path.empty() || path.back() != sg) path.push_back(sg);
+      }
+      const int c0 = cb_con_start[s2], cn = cb_con_start[s2 + 1] - c0;
+      for (int e = 0; e < cn; ++e) if (cb_con[c0 + e] != cb_con[c0] + e) ok = false;   // contiguous contacts
+      if (path.size() > 4 || cn > 15 || (cn > 0 && cb_con[c0] > 255)) ok = false;
+      if (!ok) break;
+      uint32_t pk = 0;
+      for (int j = 0; j < 4; ++j) pk |= uint32_t(j < int(path.size()) ? path[j] : 0xf) << (4 * j);
+      for (int k = 0; k < 6; ++k)
+        cb_task[s2 * 6 + k] = int32_t(pk | (uint32_t(k) << 16) | (1u << 19) | (uint32_t(cn ? cb_con[c0] : 0) << 20) | (uint32_t(cn) << 28));
+    }
+    if (ok) {
+      for (int sg = 0; sg < nseg; ++sg)
+        for (int k = 0; k < 6; ++k)
+          seg_task[sg * 6 + k] = int32_t(uint32_t(seg_d0[sg]) | (uint32_t(seg_len[sg]) << 8) | (uint32_t(k) << 12) | (1u << 15) |
+                                         (uint32_t(seg_cb0[sg]) << 16) | (uint32_t(seg_cbn[sg]) << 24));
+      for (int l = 0; l < 32; ++l) {
+        uint32_t w3 = 0;
+        for (int q = 0; q < 3; ++q) { const int d = l + 32 * q; w3 |= uint32_t(d < nv && seg_of[d] >= 0 ? seg_of[d] : 0xff) << (8 * q); }
+        dof_seg3[l] = int32_t(w3);
+      }
+      m.use_seg = 1; m.nseg = nseg;
+    }
+  }
 
   // ---- per joint floats
   auto qpos0 = b.f32("qpos0"), qpos_spring = b.f32("qpos_spring");
@@ -470,6 +532,8 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   PI(con_geom, con_geom); PI(con_side, con_side); PI(con_cb, con_cb); PF(con_par, con_par);
   PI(cb_body, cb_body); PI(cb_chain_start, cb_chain_start); PI(cb_chain_dof, cb_chain_dof); PI(dof_cb_start, dof_cb_start);
   PI(dof_cb, dof_cb); PI(cb_con_start, cb_con_start); PI(cb_con, cb_con);
+  m.seg_task = TMJX_OFF(uint32_t, push(t.i32, seg_task)); m.cb_task = TMJX_OFF(uint32_t, push(t.i32, cb_task));
+  m.dof_seg3 = TMJX_OFF(uint32_t, push(t.i32, dof_seg3));
 #undef PI
 #undef PF
 #undef P8
@@ -485,6 +549,7 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     auto tk = [&](int n) { int r = c; c += pad4(n); return r; };
     m.c_sx = tk(nv); m.c_sy = m.c_sD = 0; m.c_sV = tk(m.ncb * 6); m.c_sW = tk(m.ncon * 6); m.c_sWb = tk(m.ncb * 6);
     m.c_off = tk(m.ncon * 3); m.c_t1 = tk(m.ncon * 3); m.c_lf = tk(m.nlimit);
+    m.c_sP = tk(64);
     m.c_end = c;
     o += std::max(pad4(nbody * 10), c);
   }
@@ -521,6 +586,9 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   RF(dof_armature); RF(dof_damping);
   R8(anc_pow); R8(dsc_list);
   m.dsc_pack = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dsc_pack);
+  m.seg_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.seg_task);
+  m.cb_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.cb_task);
+  m.dof_seg3 = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dof_seg3);
   m.m_rc = d16 + reinterpret_cast<uintptr_t>(m.m_rc);
   RF(m_add1); RF(m_add2);
   m.dsc_start = d16 + reinterpret_cast<uintptr_t>(m.dsc_start);
