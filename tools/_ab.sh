@@ -3,7 +3,8 @@ OUT=gpurun_out; TAG=${1:-ab}; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -15 $OUT/${TAG}_pytest.log
 (
-  timeout 300 python tools/gpu_perf_sweep.py 148 4096 8192
-  TMJX_NO_SEG=1 timeout 300 python tools/gpu_perf_sweep.py 148 4096
+  timeout 300 python tools/gpu_perf_sweep.py 4096 8192
+  TMJX_SYNC=-1 timeout 300 python tools/gpu_perf_sweep.py 4096
+  TMJX_SYNC=1 timeout 300 python tools/gpu_perf_sweep.py 4096
 ) > $OUT/${TAG}_sweep.log 2>&1
 cat $OUT/${TAG}_sweep.log

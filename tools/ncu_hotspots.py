@@ -21,8 +21,9 @@ def main():
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
     import glob
 
-    cubin = glob.glob(tmp + "/*.cubin")[0]
-    dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout.splitlines()
+    dis = []   # one cubin per translation unit (the residency variants are separate TUs)
+    for cubin in sorted(glob.glob(tmp + "/*.cubin")):
+        dis += subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout.splitlines()
     addr2line, inside, src_file = {}, False, None
     frames, last = [], None   # marker lines since the previous instruction (innermost first)
     for ln in dis:

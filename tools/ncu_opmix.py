@@ -11,8 +11,9 @@ def main():
     nops = int(sys.argv[5]) if len(sys.argv) > 5 else 10
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
-    cubin = glob.glob(tmp + "/*.cubin")[0]
-    dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout.splitlines()
+    dis = []   # one cubin per translation unit (the residency variants are separate TUs)
+    for cubin in sorted(glob.glob(tmp + "/*.cubin")):
+        dis += subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout.splitlines()
     addr2, inside, frames, last = {}, False, [], None
     for ln in dis:
         if ln.startswith("//---") and ".text." in ln:

@@ -212,6 +212,21 @@ __device__ __forceinline__ float vdot(const float a[kNvSlots], const float b[kNv
   return wsum(s);
 }
 
+
+// 6- and 10-float records (spatial vectors, cdof rows, composite inertias) are 8-byte aligned in the slice: move them as
+// float2 (LDS.64 / STS.64 halve the shared-memory instruction count of the tree passes)
+template <int NC>
+__device__ __forceinline__ void ld_rec(const float* p, float (&v)[NC]) {
+  static_assert(NC % 2 == 0, "even record length");
+#pragma unroll
+  for (int k = 0; k < NC / 2; ++k) { const float2 t = reinterpret_cast<const float2*>(p)[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+}
+template <int NC>
+__device__ __forceinline__ void st_rec(float* p, const float (&v)[NC]) {
+#pragma unroll
+  for (int k = 0; k < NC / 2; ++k) reinterpret_cast<float2*>(p)[k] = make_float2(v[2 * k], v[2 * k + 1]);
+}
+
 // ---------------------------------------------------------------------------------------------- smooth dynamics
 // ---- log-depth tree scans (ancestor doubling).  Lane l owns bodies l, l+32, l+64 (kBodySlots).
 constexpr int kBodySlots = 3;
@@ -495,11 +510,12 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
       const int da = m.body_dofadr[b], dn = m.body_dofnum[b];
       for (int d = da; d < da + dn; ++d) {
         const float v = qvel[d];
+        float cd[6];
+        ld_rec<6>(cdof + d * 6, cd);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dv[k] += cdof[d * 6 + k] * v;
+        for (int k = 0; k < 6; ++k) dv[k] += cd[k] * v;
       }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) cvel[b * 6 + k] = dv[k];
+      st_rec<6>(cvel + b * 6, dv);
     }
   }
   __syncwarp();
@@ -512,20 +528,20 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
     if (d < m.nv) {
       const int b = m.dof_body[d], p = m.body_parent[b], j = m.dof_jnt[d], d0 = m.body_dofadr[b];
       float cv[6], t[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < 6; ++k) cv[k] = cvel[p * 6 + k];
+      ld_rec<6>(cvel + p * 6, cv);
       const bool is_free = m.jnt_type[j] == kJntFree;
       const int r = d - m.jnt_dofadr[j];
       // free joint: translations have cdof_dot = 0, the three rotations all see the velocity after the translations
       const int upto = is_free ? (r < 3 ? d0 : d0 + 3) : d;
       for (int e = d0; e < upto; ++e) {
         const float v = qvel[e];
+        float ce[6];
+        ld_rec<6>(cdof + e * 6, ce);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cv[k] += cdof[e * 6 + k] * v;
+        for (int k = 0; k < 6; ++k) cv[k] += ce[k] * v;
       }
-      if (!(is_free && r < 3)) motion_cross(cv, cdof + d * 6, t);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) cdd[d * 6 + k] = t[k];
+      if (!(is_free && r < 3)) { float cd[6]; ld_rec<6>(cdof + d * 6, cd); motion_cross(cv, cd, t); }
+      st_rec<6>(cdd + d * 6, t);
     }
   }
   __syncwarp();
@@ -538,11 +554,12 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
       const int da = m.body_dofadr[b], dn = m.body_dofnum[b];
       for (int d = da; d < da + dn; ++d) {
         const float v = qvel[d];
+        float cd[6];
+        ld_rec<6>(cdd + d * 6, cd);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) da6[k] += cdd[d * 6 + k] * v;
+        for (int k = 0; k < 6; ++k) da6[k] += cd[k] * v;
       }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = da6[k];
+      st_rec<6>(cacc + b * 6, da6);
     }
   }
   __syncwarp();
@@ -553,14 +570,18 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
   for (int s = 0; s < kBodySlots; ++s) {
     const int b = w.lane + 32 * s;
     if (b < m.nbody) {
-      float ca[6], f1[6], f2[6], f3[6];
+      float ca[6], cv[6], ci[10], f1[6], f2[6], f3[6];
+      ld_rec<6>(cacc + b * 6, ca);
+      ld_rec<6>(cvel + b * 6, cv);
+      ld_rec<10>(cin + b * 10, ci);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) ca[k] = cacc[b * 6 + k] + (k < 3 ? 0.f : -m.gravity[k - 3]);
-      inert_mul(cin + b * 10, ca, f1);
-      inert_mul(cin + b * 10, cvel + b * 6, f2);
-      motion_cross_force(cvel + b * 6, f2, f3);
+      for (int k = 3; k < 6; ++k) ca[k] = ca[k] + -m.gravity[k - 3];
+      inert_mul(ci, ca, f1);
+      inert_mul(ci, cv, f2);
+      motion_cross_force(cv, f2, f3);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) cacc[b * 6 + k] = f1[k] + f3[k];
+      for (int k = 0; k < 6; ++k) f1[k] = f1[k] + f3[k];
+      st_rec<6>(cacc + b * 6, f1);
     }
   }
   __syncwarp();
@@ -570,9 +591,11 @@ __device__ void com_vel_rne(const Warp& w, float bias[kNvSlots]) {
     const int d = w.lane + 32 * q;
     float acc = 0.f;
     if (d < m.nv) {
-      const float* cf = cacc + m.dof_body[d] * 6;
+      float cf[6], cd[6];
+      ld_rec<6>(cacc + m.dof_body[d] * 6, cf);
+      ld_rec<6>(cdof + d * 6, cd);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) acc += cdof[d * 6 + k] * cf[k];
+      for (int k = 0; k < 6; ++k) acc += cd[k] * cf[k];
     }
     bias[q] = acc;
   }
@@ -636,10 +659,11 @@ __device__ void build_m(const Warp& w) {
   float* f = L2;  // M-build scratch, dead before L2 is written
   sum_subtrees<10>(w, crb);
   for (int d = w.lane; d < m.nv; d += 32) {
-    float t[6];
-    inert_mul(crb + m.dof_body[d] * 10, cdof + d * 6, t);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) f[d * 6 + k] = t[k];
+    float t[6], ci[10], cd[6];
+    ld_rec<10>(crb + m.dof_body[d] * 10, ci);
+    ld_rec<6>(cdof + d * 6, cd);
+    inert_mul(ci, cd, t);
+    st_rec<6>(f + d * 6, t);
   }
   __syncwarp();
   __syncwarp();  // f (aliasing the o_L2 block) is complete
@@ -654,9 +678,11 @@ __device__ void build_m(const Warp& w) {
       v[it] = 0.f;
       if (e < m.nM) {
         const int rc = m.m_rc[e], i = rc & 0xff, j = rc >> 8;
-        float a = 0.f;
+        float a = 0.f, fi[6], cj[6];
+        ld_rec<6>(f + i * 6, fi);
+        ld_rec<6>(cdof + j * 6, cj);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a += f[i * 6 + k] * cdof[j * 6 + k];
+        for (int k = 0; k < 6; ++k) a += fi[k] * cj[k];
         v[it] = a + m.m_add1[e];
       }
     }
@@ -940,8 +966,9 @@ __device__ void apply_JT(const Warp& w, const Rows& r, const float f[kRowSlots],
       const int sg = (ds3 >> (8 * q)) & 0xff;
       float acc = 0.f;
       if (sg != 0xff) {
-        const float* W = sP + sg * 6;
-        const float* cd = cdof + d * 6;
+        float W[6], cd[6];
+        ld_rec<6>(sP + sg * 6, W);
+        ld_rec<6>(cdof + d * 6, cd);
 #pragma unroll
         for (int k = 0; k < 6; ++k) acc = fmaf(cd[k], W[k], acc);
       }
@@ -1402,7 +1429,7 @@ struct FwdOut {
 
 __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   const DevModel& m = w.m;
-  phase_sync();
+  if (m.sync_level >= 0) phase_sync();
   kinematics(w);
   if (m.sync_level > 1) phase_sync();
   com_pos(w, fo.com);
