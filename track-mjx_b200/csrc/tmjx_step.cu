@@ -677,13 +677,14 @@ __device__ void build_m(const Warp& w) {
       const int e = w.lane + 32 * it;
       v[it] = 0.f;
       if (e < m.nM) {
-        const int rc = m.m_rc[e], i = rc & 0xff, j = rc >> 8;
+        const uint32_t rc = (m.m_rc2[w.lane + 32 * (it >> 1)] >> (16 * (it & 1))) & 0xffffu;
+        const int i = rc & 0xff, j = rc >> 8;
         float a = 0.f, fi[6], cj[6];
         ld_rec<6>(f + i * 6, fi);
         ld_rec<6>(cdof + j * 6, cj);
 #pragma unroll
         for (int k = 0; k < 6; ++k) a += fi[k] * cj[k];
-        v[it] = a + m.m_add1[e];
+        v[it] = a;
       }
     }
     __syncwarp();  // f is dead from here
@@ -692,9 +693,22 @@ __device__ void build_m(const Warp& w) {
       const int e = w.lane + 32 * it;
       if (e < m.nM) {
         L1[e] = v[it];
-        L2[e] = v[it] + m.m_add2[e];
+        L2[e] = v[it];
         if (m.o_L != m.o_big) w.at(m.o_L)[e] = v[it];  // Newton: the raw inertia stays at o_big, its copy is factored
       }
+    }
+  }
+  __syncwarp();
+  // diagonal: + armature (all copies), + dt * damping (the Euler matrix)
+#pragma unroll
+  for (int q = 0; q < kNvSlots; ++q) {
+    const int d = w.lane + 32 * q;
+    if (d < m.nv) {
+      const int e = w.rend[q] - w.dep[q];
+      const float vd = L1[e] + m.dof_armature[d];
+      L1[e] = vd;
+      L2[e] = vd + __fmul_rn(m.dt, m.dof_damping[d]);
+      if (m.o_L != m.o_big) w.at(m.o_L)[e] = vd;
     }
   }
   __syncwarp();
@@ -1197,9 +1211,15 @@ __device__ void build_hessian(const Warp& w, const Rows& r, const float Jaref[kR
 // ---------------------------------------------------------------------------------------------- solver.solve (CG)
 struct LSPoint { float alpha, cost, d0, d1; };
 
+// One line-search evaluation at N step sizes.  solver.py sums the per-row quadratic coefficients
+// (q0, q1, q2) = (D Jaref^2 / 2, D jv Jaref, D jv^2 / 2) of the active rows and evaluates cost = a^2 q2 + a q1 + q0 and its
+// derivatives; with t = Jaref + a jv (which the activity test needs anyway) the same three sums are
+//   cost = sum D t^2 / 2,   d/da = sum D t jv,   d2/da2 = sum D jv^2
+// -- identical in exact arithmetic, one FMUL + two predicated FFMA + one predicated FADD per (row, point) and two
+// registers per row (Dj = D jv, Djj = D jv^2) instead of three.
 template <int N>
 __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float Jaref[kRowSlots], const float jv[kRowSlots],
-                                          const float q0[kRowSlots], const float q1[kRowSlots], const float q2[kRowSlots],
+                                          const float D[kRowSlots], const float Dj[kRowSlots], const float Djj[kRowSlots],
                                           const float qg[3], LSPoint (&out)[N]) {
   float a0[N], a1[N], a2[N];
 #pragma unroll
@@ -1207,8 +1227,9 @@ __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float J
     a0[p] = a1[p] = a2[p] = 0.f;
 #pragma unroll
     for (int k = 0; k < kRowSlots; ++k) {
-      // three predicated FADDs (the select form compiled to FSEL + FADD pairs)
-      if ((Jaref[k] + alpha[p] * jv[k]) < 0.f) { a0[p] += q0[k]; a1[p] += q1[k]; a2[p] += q2[k]; }
+      const float t = Jaref[k] + alpha[p] * jv[k];
+      const float u = D[k] * t;
+      if (t < 0.f) { a0[p] = fmaf(u, t, a0[p]); a1[p] = fmaf(Dj[k], t, a1[p]); a2[p] += Djj[k]; }
     }
   }
   if constexpr (N == 3) {
@@ -1228,11 +1249,12 @@ __device__ __forceinline__ void ls_points(const float (&alpha)[N], const float J
   }
 #pragma unroll
   for (int p = 0; p < N; ++p) {
-    const float t0 = a0[p] + qg[0], t1 = a1[p] + qg[1], t2 = a2[p] + qg[2], a = alpha[p];
+    const float a = alpha[p];
+    const float q2 = qg[2] + 0.5f * a2[p];   // the total quadratic coefficient (solver.py quad_total[2])
     out[p].alpha = a;
-    out[p].cost = a * a * t2 + a * t1 + t0;
-    out[p].d0 = 2.f * a * t2 + t1;
-    out[p].d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
+    out[p].cost = 0.5f * a0[p] + (a * a * qg[2] + a * qg[1] + qg[0]);
+    out[p].d0 = a1[p] + (2.f * a * qg[2] + qg[1]);
+    out[p].d1 = 2.f * q2 + (q2 == 0.f ? kMinVal : 0.f);
   }
 }
 
@@ -1347,21 +1369,17 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
       for (int q = 0; q < kNvSlots; ++q) { a += search[q] * Ma[q]; b += search[q] * qfs[q]; c += search[q] * mv[q]; }
       qg[0] = gauss; qg[1] = wsum(a) - wsum(b); qg[2] = 0.5f * wsum(c);
     }
-    float q0[kRowSlots], q1[kRowSlots], q2[kRowSlots];
+    float Dj[kRowSlots], Djj[kRowSlots];
 #pragma unroll
-    for (int k = 0; k < kRowSlots; ++k) {
-      q0[k] = 0.5f * Jaref[k] * Jaref[k] * r.D[k];
-      q1[k] = jv[k] * Jaref[k] * r.D[k];
-      q2[k] = 0.5f * jv[k] * jv[k] * r.D[k];
-    }
+    for (int k = 0; k < kRowSlots; ++k) { Dj[k] = r.D[k] * jv[k]; Djj[k] = Dj[k] * jv[k]; }
     LSPoint p0, lo, hi;
     {
       const float a0[1] = {0.f};
       LSPoint o1[1];
-      ls_points<1>(a0, Jaref, jv, q0, q1, q2, qg, o1);
+      ls_points<1>(a0, Jaref, jv, r.D, Dj, Djj, qg, o1);
       p0 = o1[0];
       const float a1[1] = {p0.alpha - p0.d0 / p0.d1};
-      ls_points<1>(a1, Jaref, jv, q0, q1, q2, qg, o1);
+      ls_points<1>(a1, Jaref, jv, r.D, Dj, Djj, qg, o1);
       lo = o1[0];
       const bool lesser = lo.d0 < p0.d0;
       hi = lesser ? p0 : lo;
@@ -1376,7 +1394,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
       if (done) break;
       const float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
       LSPoint o3[3];
-      ls_points<3>(al, Jaref, jv, q0, q1, q2, qg, o3);
+      ls_points<3>(al, Jaref, jv, r.D, Dj, Djj, qg, o3);
       const LSPoint lo_next = o3[0], hi_next = o3[1], mid = o3[2];
       const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
       if (swap_lo_next) lo = lo_next;

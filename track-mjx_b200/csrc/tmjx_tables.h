@@ -54,9 +54,9 @@ struct DevModel {
   /* dsc_pack[r * nbody + b] = count << 16 | (count == 1 ? the descendant : first index into dsc_list): one load per
    * (round, body) on the common path (chains: at most one descendant at each distance) */
   const uint32_t* dsc_pack;
-  /* per sparse-inertia entry: row | col << 8, and the two diagonal additions (armature; armature + dt * damping) */
-  const uint16_t* m_rc;
-  const float *m_add1, *m_add2;
+  /* per sparse-inertia entry e = lane + 32 it: row | col << 8, two iterations per word:
+   * m_rc2[lane + 32 h] = rc[lane + 32 (2 h)] | rc[lane + 32 (2 h + 1)] << 16 */
+  const uint32_t* m_rc2;
   // ---- per joint
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_body;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_qpos0, *jnt_springref;
@@ -505,15 +505,14 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   P8(anc_pow, anc_pow); P8(dsc_list, dsc_list);
   m.dsc_pack = TMJX_OFF(uint32_t, push(t.i32, dsc_pack));
   {
-    auto arm = b.f32("dof_armature"), damp = b.f32("dof_damping");
-    std::vector<uint16_t> rc(m.nM);
-    std::vector<float> add1(m.nM, 0.f), add2(m.nM, 0.f);
+    if (m.nM > 1280) throw std::runtime_error("more than 1280 inertia entries unsupported");
+    std::vector<int32_t> rc2(32 * 20, 0);
     for (int e = 0; e < m.nM; ++e) {
-      rc[e] = uint16_t(m_row[e] | (m_col[e] << 8));
-      if (m_row[e] == m_col[e]) { add1[e] = arm[m_row[e]]; add2[e] = m.dt * damp[m_row[e]]; }
+      const uint32_t rc = uint32_t(m_row[e]) | (uint32_t(m_col[e]) << 8);
+      const int lane = e & 31, it = e >> 5;
+      rc2[lane + 32 * (it >> 1)] |= int32_t(rc << (16 * (it & 1)));
     }
-    m.m_rc = TMJX_OFF(uint16_t, push(t.u16, rc));
-    PF(m_add1, add1); PF(m_add2, add2);
+    m.m_rc2 = TMJX_OFF(uint32_t, push(t.i32, rc2));
   }
   m.dsc_start = TMJX_OFF(uint16_t, push(t.u16, dsc_start));
   P8(m_anc, m_anc); P8(m_row, m_row); P8(m_col, m_col); P8(tri_a, tri_a); P8(tri_b, tri_b);
@@ -589,8 +588,7 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   m.seg_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.seg_task);
   m.cb_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.cb_task);
   m.dof_seg3 = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dof_seg3);
-  m.m_rc = d16 + reinterpret_cast<uintptr_t>(m.m_rc);
-  RF(m_add1); RF(m_add2);
+  m.m_rc2 = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.m_rc2);
   m.dsc_start = d16 + reinterpret_cast<uintptr_t>(m.dsc_start);
   R8(m_anc); R8(m_row); R8(m_col); R8(tri_a); R8(tri_b);
   m.dmask = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dmask);
