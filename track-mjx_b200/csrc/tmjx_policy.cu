@@ -1,0 +1,451 @@
+/*
+ * tmjx_policy.cu — in-loop intention-network inference for the tracking env (BASELINE configs[2]).
+ *
+ * Replaces, for the acting loop only (no gradients),
+ *   IntentionNetwork.__call__ / Encoder / Decoder / reparameterize   reference track_mjx/agent/mlp_ppo/intention_network.py:14-142
+ *   make_inference_fn().policy (sample, log_prob, postprocess)       reference track_mjx/agent/mlp_ppo/ppo_networks.py:34-100
+ *   running_statistics.normalize                                     reference track_mjx/agent/masked_running_statistics.py:217-236
+ *   NormalTanhDistribution (upstream brax 0.12.3 training/distribution.py: scale = softplus(raw) + 0.001, tanh bijector)
+ *
+ * B200 mapping: every Dense layer is one tcgen05 GEMM over the environment batch -- `tcgen05.mma.cta_group::1.kind::tf32`
+ * (fp32 operands read as TF32 by the tensor core, fp32 accumulation in TMEM; XLA's default fp32 matmul precision on
+ * NVIDIA GPUs is TF32 as well), 128 x 128 output tiles, one elected thread issues the MMAs, operands are staged in shared
+ * memory by a 3-deep cp.async ring in the canonical no-swizzle K-major core-matrix layout, stage reuse is tracked by
+ * `tcgen05.commit` on mbarriers, the epilogue reads the accumulator with `tcgen05.ld` (thread = output row), adds the
+ * bias, applies SiLU and writes fp32 activations.  LayerNorm, observation normalisation, the reparameterised latent and
+ * the tanh-normal action head are small row-wise kernels around the GEMMs.  All launches are enqueued on the caller's
+ * stream; nothing is allocated per call.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tmjx.h"
+
+namespace tmjx_policy {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, THREADS = 256;
+constexpr int kStageBytes = (BM + BN) * BK * 4;
+constexpr int kSmemBytes = STAGES * kStageBytes;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format, version 1): 8 x 16 B core matrices, LBO = byte
+// distance between the two core matrices an MMA reads along K, SBO = byte distance between 8-row groups along M / N
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// Y[M, ldy] (columns n0 .. n0 + 127 of this block) = act(X[M, K] * Wt[N, K]^T + bias).  X / Wt row pitches ldx / ldw are
+// multiples of BK floats and zero padded; Wt and bias are padded to a multiple of BN rows.
+__global__ void __launch_bounds__(THREADS) linear_tf32_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Wt, int ldw,
+                                                              const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
+                                                              int act, int desc_swap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_free[STAGES];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nk = Kpad / BK;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(uint32_t(BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bar_free[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  // one stage = A tile then B tile, each stored chunk-major: 16-byte K chunk kc of row r at (kc * ROWS + r) * 16
+  auto load_stage = [&](int kt, int s) {
+    const uint32_t sa = sbase + s * kStageBytes, sb = sa + BM * BK * 4;
+#pragma unroll
+    for (int i = 0; i < (BM + BN) * (BK / 4) / THREADS; ++i) {
+      const int c = tid + THREADS * i;
+      if (c < BM * (BK / 4)) {
+        const int r = c >> 3, kc = c & 7;
+        const bool ok = m0 + r < M;
+        const float* src = X + size_t(ok ? m0 + r : 0) * ldx + kt * BK + kc * 4;
+        cp_async16(sa + (kc * BM + r) * 16, src, ok ? 16u : 0u);
+      } else {
+        const int c2 = c - BM * (BK / 4), r = c2 >> 3, kc = c2 & 7;
+        const float* src = Wt + size_t(n0 + r) * ldw + kt * BK + kc * 4;
+        cp_async16(sb + (kc * BN + r) * 16, src, 16u);
+      }
+    }
+  };
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % STAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = sbase + s * kStageBytes, sb = sa + BM * BK * 4;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {   // one MMA = K 8 (two 16-byte chunks)
+        const uint32_t a_lbo = desc_swap ? 128u : uint32_t(BM * 16), a_sbo = desc_swap ? uint32_t(BM * 16) : 128u;
+        const uint32_t b_lbo = desc_swap ? 128u : uint32_t(BN * 16), b_sbo = desc_swap ? uint32_t(BN * 16) : 128u;
+        const uint64_t da = make_desc(sa + j * 2 * BM * 16, a_lbo, a_sbo);
+        const uint64_t db = make_desc(sb + j * 2 * BN * 16, b_lbo, b_sbo);
+        mma_tf32(tmem, da, db, idesc, (kt > 0 || j > 0) ? 1u : 0u);
+      }
+      mma_commit(&bar_free[s]);   // arrives when the MMAs above (and all earlier ones) have read their operands and finished
+    }
+    const int kn = kt + STAGES - 1;
+    if (kn < nk) {
+      const int sn = kn % STAGES;
+      if (kt >= 1) mbar_wait(&bar_free[sn], uint32_t(((kt - 1) / STAGES) & 1));   // iteration kt - 1 read stage sn
+      load_stage(kn, sn);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  mbar_wait(&bar_free[(nk - 1) % STAGES], uint32_t(((nk - 1) / STAGES) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), column half w / 4
+  const int lane_base = (warp & 3) * 32, col_base = (warp >> 2) * 64;
+  const int row = m0 + lane_base + lane;
+#pragma unroll
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + (uint32_t(lane_base) << 16) + uint32_t(col_base + c);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < M) {
+      float* dst = Y + size_t(row) * ldy + n0 + col_base + c;
+      const float* bb = bias + n0 + col_base + c;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = __uint_as_float(v[j]) + __ldg(bb + j);
+        o.y = __uint_as_float(v[j + 1]) + __ldg(bb + j + 1);
+        o.z = __uint_as_float(v[j + 2]) + __ldg(bb + j + 2);
+        o.w = __uint_as_float(v[j + 3]) + __ldg(bb + j + 3);
+        if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(BN)) : "memory");
+}
+
+// flax nn.LayerNorm (epsilon 1e-6, use_fast_variance: var = E[x^2] - E[x]^2 clipped at 0), in place; one warp per row
+__global__ void layernorm_kernel(float* __restrict__ Y, int ldy, int n, const float* __restrict__ scale, const float* __restrict__ bias, int M) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float* y = Y + size_t(row) * ldy;
+  float s = 0.f, s2 = 0.f;
+  for (int i = lane * 4; i < n; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(y + i);
+    s += v.x + v.y + v.z + v.w;
+    s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const float mean = s / float(n), var = fmaxf(0.f, s2 / float(n) - mean * mean), rstd = rsqrtf(var + 1e-6f);
+  for (int i = lane * 4; i < n; i += 128) {
+    float4 v = *reinterpret_cast<const float4*>(y + i);
+    const float4 g = *reinterpret_cast<const float4*>(scale + i), b = *reinterpret_cast<const float4*>(bias + i);
+    v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
+    v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+    *reinterpret_cast<float4*>(y + i) = v;
+  }
+}
+
+// (obs - mean) / std; reference part -> encoder input [M, ld_enc], proprioceptive part -> decoder input columns latent..
+__global__ void obs_prep_kernel(const float* __restrict__ obs, int nobs, int nref, int latent, const float* __restrict__ mean,
+                                const float* __restrict__ stdv, float* __restrict__ enc_in, int ld_enc, float* __restrict__ dec_in, int ld_dec, int M) {
+  const int row = blockIdx.x;
+  if (row >= M) return;
+  const float* o = obs + size_t(row) * nobs;
+  for (int i = threadIdx.x; i < nobs; i += blockDim.x) {
+    const float v = (o[i] - mean[i]) / stdv[i];
+    if (i < nref) enc_in[size_t(row) * ld_enc + i] = v;
+    else dec_in[size_t(row) * ld_dec + latent + (i - nref)] = v;
+  }
+}
+
+// z = mean + exp(logvar / 2) * eps (or the mean when deterministic) into decoder input columns 0 .. latent - 1
+__global__ void latent_kernel(const float* __restrict__ head, int ld_head, int latent, const float* __restrict__ eps, int deterministic,
+                              float* __restrict__ dec_in, int ld_dec, float* __restrict__ out_mean, float* __restrict__ out_logvar, int M) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * latent) return;
+  const int row = idx / latent, j = idx % latent;
+  const float mu = head[size_t(row) * ld_head + j], lv = head[size_t(row) * ld_head + latent + j];
+  const float z = deterministic ? mu : mu + eps[idx] * expf(0.5f * lv);
+  dec_in[size_t(row) * ld_dec + j] = z;
+  if (out_mean) out_mean[idx] = mu;
+  if (out_logvar) out_logvar[idx] = lv;
+}
+
+// NormalTanhDistribution: loc, scale = softplus(raw) + 0.001; raw_action = loc + scale * eps; action = tanh(raw_action);
+// log_prob = sum_i [ N(raw; loc, scale) - log|d tanh / d raw| ],  log|.| = 2 (log 2 - x - softplus(-2 x))
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__global__ void action_head_kernel(const float* __restrict__ lg, int ld_lg, int na, const float* __restrict__ eps, int deterministic,
+                                   float* __restrict__ action, float* __restrict__ raw_action, float* __restrict__ log_prob,
+                                   float* __restrict__ logits, int M) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* l = lg + size_t(row) * ld_lg;
+  float lp = 0.f;
+  for (int i = lane; i < na; i += 32) {
+    const float loc = l[i], scale = softplus(l[na + i]) + 0.001f;
+    const float raw = deterministic ? loc : loc + scale * eps[size_t(row) * na + i];
+    action[size_t(row) * na + i] = tanhf(raw);
+    if (raw_action) raw_action[size_t(row) * na + i] = raw;
+    const float zn = (raw - loc) / scale;
+    lp += -0.5f * zn * zn - logf(scale) - 0.91893853320467274f - 2.f * (0.69314718055994531f - raw - softplus(-2.f * raw));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+  if (log_prob && lane == 0) log_prob[row] = lp;
+  if (logits) for (int i = lane; i < 2 * na; i += 32) logits[size_t(row) * 2 * na + i] = l[i];
+}
+
+struct Layer {
+  int k = 0, n = 0, kpad = 0, npad = 0, act = 0, ln = 0;
+  float *wt = nullptr, *bias = nullptr, *ln_scale = nullptr, *ln_bias = nullptr;
+};
+
+}  // namespace tmjx_policy
+
+using namespace tmjx_policy;
+
+struct TmjxPolicy {
+  TmjxPolicyDesc d;
+  int device = 0, max_env = 0, desc_swap = 0;
+  std::vector<Layer> enc, dec;   // enc: hidden layers + the fused (mean | logvar) head; dec: hidden layers + logits
+  float *norm_mean = nullptr, *norm_std = nullptr;
+  float* buf[2] = {nullptr, nullptr};   // ping-pong activations [max_env, ld_buf]
+  float *enc_in = nullptr, *dec_in = nullptr;
+  int ld_buf = 0, ld_enc = 0, ld_dec = 0;
+  std::vector<void*> owned;
+};
+
+static thread_local std::string g_perr;
+static int pfail(int code, const std::string& msg) { g_perr = msg; return code; }
+#define PCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return pfail(TMJX_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+static int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+extern "C" {
+
+const char* tmjx_policy_last_error(void) { return g_perr.c_str(); }
+
+size_t tmjx_policy_param_count(const TmjxPolicyDesc* d) {
+  if (!d) return 0;
+  size_t n = 2 * size_t(d->obs_size);
+  int k = d->reference_obs_size;
+  for (int i = 0; i < d->n_encoder_layers; ++i) { n += size_t(k) * d->encoder_layers[i] + 3 * size_t(d->encoder_layers[i]); k = d->encoder_layers[i]; }
+  n += 2 * (size_t(k) * d->latent_size + d->latent_size);
+  k = d->latent_size + d->obs_size - d->reference_obs_size;
+  for (int i = 0; i < d->n_decoder_layers; ++i) { n += size_t(k) * d->decoder_layers[i] + 3 * size_t(d->decoder_layers[i]); k = d->decoder_layers[i]; }
+  n += size_t(k) * 2 * d->action_size + 2 * d->action_size;
+  return n;
+}
+
+int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_params, int device, int max_env, TmjxPolicy** out) {
+  if (!d || !params || !out || max_env <= 0) return pfail(TMJX_E_ARG, "null argument");
+  if (d->n_encoder_layers < 1 || d->n_encoder_layers > TMJX_POLICY_MAX_LAYERS || d->n_decoder_layers < 1 || d->n_decoder_layers > TMJX_POLICY_MAX_LAYERS)
+    return pfail(TMJX_E_ARG, "layer count out of range");
+  if (n_params != tmjx_policy_param_count(d)) return pfail(TMJX_E_ARG, "parameter vector has the wrong length");
+  PCU(cudaSetDevice(device));
+  auto* p = new TmjxPolicy();
+  p->d = *d; p->device = device; p->max_env = max_env;
+  if (const char* e = std::getenv("TMJX_POLICY_DESC_SWAP")) p->desc_swap = atoi(e);
+  const float* cur = params;
+  auto upload = [&](const std::vector<float>& h, float** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(h.size(), 1) * 4);
+    if (e != cudaSuccess) return e;
+    p->owned.push_back(*dst);
+    return cudaMemcpy(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  };
+  {
+    std::vector<float> m(cur, cur + d->obs_size); cur += d->obs_size;
+    std::vector<float> s(cur, cur + d->obs_size); cur += d->obs_size;
+    PCU(upload(m, &p->norm_mean)); PCU(upload(s, &p->norm_std));
+  }
+  // W is flax's Dense kernel [in, out] row-major; the tensor core wants both operands K-major: Wt[out (padded), in (padded)]
+  auto dense = [&](int k, int n, const float* W, const float* b, Layer& L) -> cudaError_t {
+    L.k = k; L.n = n; L.kpad = pad_to(k, BK); L.npad = pad_to(n, BN);
+    std::vector<float> wt(size_t(L.npad) * L.kpad, 0.f), bb(L.npad, 0.f);
+    for (int i = 0; i < k; ++i) for (int j = 0; j < n; ++j) wt[size_t(j) * L.kpad + i] = W[size_t(i) * n + j];
+    for (int j = 0; j < n; ++j) bb[j] = b[j];
+    cudaError_t e = upload(wt, &L.wt);
+    if (e != cudaSuccess) return e;
+    return upload(bb, &L.bias);
+  };
+  auto hidden = [&](int k, int n, Layer& L) -> cudaError_t {
+    const float* W = cur; cur += size_t(k) * n;
+    const float* b = cur; cur += n;
+    cudaError_t e = dense(k, n, W, b, L);
+    if (e != cudaSuccess) return e;
+    L.act = 1; L.ln = 1;
+    std::vector<float> g(cur, cur + n); cur += n;
+    std::vector<float> be(cur, cur + n); cur += n;
+    g.resize(L.npad, 0.f); be.resize(L.npad, 0.f);
+    e = upload(g, &L.ln_scale);
+    if (e != cudaSuccess) return e;
+    return upload(be, &L.ln_bias);
+  };
+  int k = d->reference_obs_size, widest = 0;
+  for (int i = 0; i < d->n_encoder_layers; ++i) {
+    Layer L; PCU(hidden(k, d->encoder_layers[i], L)); p->enc.push_back(L); k = d->encoder_layers[i]; widest = std::max(widest, L.npad);
+  }
+  {  // fc2_mean | fc2_logvar fused into one GEMM: columns 0 .. latent-1 mean, latent .. 2 latent - 1 logvar
+    const int lat = d->latent_size;
+    const float* Wm = cur; cur += size_t(k) * lat; const float* bm = cur; cur += lat;
+    const float* Wl = cur; cur += size_t(k) * lat; const float* bl = cur; cur += lat;
+    std::vector<float> W(size_t(k) * 2 * lat), b(2 * lat);
+    for (int i = 0; i < k; ++i) for (int j = 0; j < lat; ++j) { W[size_t(i) * 2 * lat + j] = Wm[size_t(i) * lat + j]; W[size_t(i) * 2 * lat + lat + j] = Wl[size_t(i) * lat + j]; }
+    for (int j = 0; j < lat; ++j) { b[j] = bm[j]; b[lat + j] = bl[j]; }
+    Layer L; PCU(dense(k, 2 * lat, W.data(), b.data(), L)); p->enc.push_back(L); widest = std::max(widest, L.npad);
+  }
+  k = d->latent_size + d->obs_size - d->reference_obs_size;
+  for (int i = 0; i < d->n_decoder_layers; ++i) {
+    Layer L; PCU(hidden(k, d->decoder_layers[i], L)); p->dec.push_back(L); k = d->decoder_layers[i]; widest = std::max(widest, L.npad);
+  }
+  {
+    const int n = 2 * d->action_size;
+    const float* W = cur; cur += size_t(k) * n; const float* b = cur; cur += n;
+    Layer L; PCU(dense(k, n, W, b, L)); p->dec.push_back(L); widest = std::max(widest, L.npad);
+  }
+  p->ld_buf = widest;
+  p->ld_enc = pad_to(d->reference_obs_size, BK);
+  p->ld_dec = pad_to(d->latent_size + d->obs_size - d->reference_obs_size, BK);
+  for (int i = 0; i < 2; ++i) { PCU(cudaMalloc(&p->buf[i], size_t(max_env) * p->ld_buf * 4)); p->owned.push_back(p->buf[i]); PCU(cudaMemset(p->buf[i], 0, size_t(max_env) * p->ld_buf * 4)); }
+  PCU(cudaMalloc(&p->enc_in, size_t(max_env) * p->ld_enc * 4)); p->owned.push_back(p->enc_in);
+  PCU(cudaMalloc(&p->dec_in, size_t(max_env) * p->ld_dec * 4)); p->owned.push_back(p->dec_in);
+  PCU(cudaMemset(p->enc_in, 0, size_t(max_env) * p->ld_enc * 4));   // the K padding columns stay zero
+  PCU(cudaMemset(p->dec_in, 0, size_t(max_env) * p->ld_dec * 4));
+  PCU(cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  *out = p;
+  return TMJX_OK;
+}
+
+void tmjx_policy_destroy(TmjxPolicy* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (void* q : p->owned) cudaFree(q);
+  delete p;
+}
+
+static int run_linear(const TmjxPolicy* p, const Layer& L, const float* x, int ldx, float* y, int ldy, int M, cudaStream_t st) {
+  dim3 grid((M + BM - 1) / BM, L.npad / BN);
+  linear_tf32_kernel<<<grid, THREADS, kSmemBytes, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act, p->desc_swap);
+  if (L.ln) layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(y, ldy, L.n, L.ln_scale, L.ln_bias, M);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+/* plain GEMM entry point (tests, microbenchmarks): y[M, ldy] = x[M, k] * W + b through the same tcgen05 kernel */
+int tmjx_policy_linear(const TmjxPolicy* p, int which /* 0.. : encoder layers then decoder layers */, const float* x, int ldx, float* y, int ldy,
+                       int n_env, void* stream) {
+  if (!p || !x || !y) return pfail(TMJX_E_ARG, "null argument");
+  const int ne = int(p->enc.size());
+  if (which < 0 || which >= ne + int(p->dec.size())) return pfail(TMJX_E_ARG, "layer index out of range");
+  const Layer& L = which < ne ? p->enc[which] : p->dec[which - ne];
+  if (ldx < L.kpad || ldy < L.npad) return pfail(TMJX_E_ARG, "row pitch smaller than the padded layer width");
+  PCU(cudaSetDevice(p->device));
+  return run_linear(p, L, x, ldx, y, ldy, n_env, static_cast<cudaStream_t>(stream));
+}
+
+int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_latent, const float* eps_action, int deterministic, float* action,
+                    float* raw_action, float* log_prob, float* logits, float* latent_mean, float* latent_logvar, int n_env, void* stream) {
+  if (!p || !obs || !action) return pfail(TMJX_E_ARG, "null argument");
+  if (!deterministic && (!eps_latent || !eps_action)) return pfail(TMJX_E_ARG, "stochastic acting needs eps_latent and eps_action");
+  if (n_env <= 0 || n_env > p->max_env) return pfail(TMJX_E_ARG, "n_env exceeds the policy's max_env");
+  PCU(cudaSetDevice(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TmjxPolicyDesc& d = p->d;
+  obs_prep_kernel<<<n_env, 256, 0, st>>>(obs, d.obs_size, d.reference_obs_size, d.latent_size, p->norm_mean, p->norm_std, p->enc_in, p->ld_enc,
+                                         p->dec_in, p->ld_dec, n_env);
+  const float* x = p->enc_in;
+  int ldx = p->ld_enc, pp = 0;
+  for (const Layer& L : p->enc) {
+    int rc = run_linear(p, L, x, ldx, p->buf[pp], p->ld_buf, n_env, st);
+    if (rc) return rc;
+    x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
+  }
+  latent_kernel<<<(n_env * d.latent_size + 255) / 256, 256, 0, st>>>(x, ldx, d.latent_size, eps_latent, deterministic, p->dec_in, p->ld_dec,
+                                                                      latent_mean, latent_logvar, n_env);
+  x = p->dec_in; ldx = p->ld_dec;
+  for (const Layer& L : p->dec) {
+    int rc = run_linear(p, L, x, ldx, p->buf[pp], p->ld_buf, n_env, st);
+    if (rc) return rc;
+    x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
+  }
+  action_head_kernel<<<(n_env + 7) / 8, 256, 0, st>>>(x, ldx, d.action_size, eps_action, deterministic, action, raw_action, log_prob, logits, n_env);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+int tmjx_policy_launches_per_act(const TmjxPolicy* p) {
+  if (!p) return 0;
+  int n = 3;   // obs_prep, latent, action_head
+  for (const Layer& L : p->enc) n += 1 + L.ln;
+  for (const Layer& L : p->dec) n += 1 + L.ln;
+  return n;
+}
+
+}  // extern "C"
