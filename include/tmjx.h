@@ -185,6 +185,44 @@ int tmjx_step(const TmjxModel* m, const TmjxClips* c, const float* action, TmjxS
 /* FP32 FMA-throughput microbenchmark used as the roofline denominator (returns TFLOP/s, <0 on error). */
 double tmjx_fp32_peak_tflops(int device, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * In-loop policy inference (the acting half of PPO; BASELINE configs[2]).  Replaces, for inference only,
+ *   IntentionNetwork.__call__ / Encoder / Decoder   reference track_mjx/agent/mlp_ppo/intention_network.py:14-142
+ *   make_inference_fn().policy                      reference track_mjx/agent/mlp_ppo/ppo_networks.py:34-100
+ *   running_statistics.normalize                    reference track_mjx/agent/masked_running_statistics.py:217-236
+ * Dense layers run on the tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM).
+ *
+ * `params` is ONE host fp32 vector, in this order (W = flax Dense kernel [in, out] row-major):
+ *   normaliser mean[obs], std[obs];
+ *   encoder hidden_i: W, b, LayerNorm scale, LayerNorm bias   (i = 0 .. n_encoder_layers-1);
+ *   fc2_mean W, b; fc2_logvar W, b;
+ *   decoder hidden_i: W, b, LayerNorm scale, LayerNorm bias   (i = 0 .. n_decoder_layers-1);
+ *   decoder output W [., 2 action_size], b.
+ * Noise is supplied by the caller (eps ~ N(0,1); the reference draws it with jax.random inside the policy), so the
+ * call is a pure function of its inputs.  All array arguments of tmjx_policy_act are DEVICE pointers, row-major. */
+#define TMJX_POLICY_MAX_LAYERS 8
+typedef struct TmjxPolicyDesc {
+  int32_t obs_size, reference_obs_size, latent_size, action_size;
+  int32_t n_encoder_layers, encoder_layers[TMJX_POLICY_MAX_LAYERS];
+  int32_t n_decoder_layers, decoder_layers[TMJX_POLICY_MAX_LAYERS];   /* hidden sizes; the 2*action_size output is implied */
+} TmjxPolicyDesc;
+typedef struct TmjxPolicy TmjxPolicy;
+
+size_t tmjx_policy_param_count(const TmjxPolicyDesc* d);
+int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_params, int device, int max_env, TmjxPolicy** out);
+void tmjx_policy_destroy(TmjxPolicy* p);
+const char* tmjx_policy_last_error(void);
+/* obs [n_env, obs_size] -> action [n_env, action_size] (tanh-squashed).  Optional outputs may be NULL:
+ * raw_action [n_env, action_size], log_prob [n_env], logits [n_env, 2 action_size], latent_mean / latent_logvar
+ * [n_env, latent_size].  deterministic != 0: z = latent mean, action = tanh(loc) (eps may then be NULL). */
+int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_latent, const float* eps_action, int deterministic,
+                    float* action, float* raw_action, float* log_prob, float* logits, float* latent_mean, float* latent_logvar,
+                    int n_env, void* stream);
+/* one Dense (+ SiLU + LayerNorm for hidden layers) through the same tensor-core kernel; layers are numbered encoder
+ * hidden.., (mean|logvar), decoder hidden.., logits.  x [n_env, ldx], y [n_env, ldy]; pitches >= the padded widths. */
+int tmjx_policy_linear(const TmjxPolicy* p, int which, const float* x, int ldx, float* y, int ldy, int n_env, void* stream);
+int tmjx_policy_launches_per_act(const TmjxPolicy* p);
+
 #ifdef __cplusplus
 }
 #endif

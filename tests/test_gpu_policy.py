@@ -1,0 +1,125 @@
+"""GPU parity of the tcgen05 intention-network inference (csrc/tmjx_policy.cu) against a plain PyTorch fp32 restatement of
+the reference network (intention_network.py:14-142, ppo_networks.py:34-100).
+
+Tolerances: the Dense layers run as TF32 tensor-core MMAs with fp32 accumulation (the arithmetic class XLA uses for fp32
+matmuls on NVIDIA GPUs by default); the hardware truncates the fp32 operands to 10 mantissa bits, i.e. a relative error
+of <= 2^-10 per product and ~1e-3 after a 512..1024-long reduction of O(1) terms, renormalised by every LayerNorm.
+A single layer is checked to 4e-3 (abs, on O(1) outputs), the 11-layer stack to 2e-2 on logits / latents.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def torch_reference(cfg, p, obs, eps_z, eps_a, deterministic=False):
+    """fp32 restatement of IntentionNetwork.__call__ + NormalTanhDistribution (allow_tf32 off)."""
+    F = torch.nn.functional
+    t = lambda k: torch.from_numpy(p[k]).to(obs.device)
+    x = (obs - t("norm/mean")) / t("norm/std")
+    h = x[:, : cfg.reference_obs_size]
+    for i, n in enumerate(cfg.encoder_layers):
+        h = h @ t(f"encoder/hidden_{i}/kernel") + t(f"encoder/hidden_{i}/bias")
+        h = F.silu(h)
+        h = F.layer_norm(h, (n,), t(f"encoder/LayerNorm_{i}/scale"), t(f"encoder/LayerNorm_{i}/bias"), eps=1e-6)
+    mean = h @ t("encoder/fc2_mean/kernel") + t("encoder/fc2_mean/bias")
+    logvar = h @ t("encoder/fc2_logvar/kernel") + t("encoder/fc2_logvar/bias")
+    z = mean if deterministic else mean + eps_z * torch.exp(0.5 * logvar)
+    h = torch.cat([z, x[:, cfg.reference_obs_size:]], dim=-1)
+    nd = len(cfg.decoder_layers)
+    for i, n in enumerate(cfg.decoder_layers):
+        h = h @ t(f"decoder/hidden_{i}/kernel") + t(f"decoder/hidden_{i}/bias")
+        h = F.silu(h)
+        h = F.layer_norm(h, (n,), t(f"decoder/LayerNorm_{i}/scale"), t(f"decoder/LayerNorm_{i}/bias"), eps=1e-6)
+    logits = h @ t(f"decoder/hidden_{nd}/kernel") + t(f"decoder/hidden_{nd}/bias")
+    loc, raw_scale = logits[:, : cfg.action_size], logits[:, cfg.action_size:]
+    scale = F.softplus(raw_scale) + 0.001
+    raw = loc if deterministic else loc + scale * eps_a
+    logp = (-0.5 * ((raw - loc) / scale) ** 2 - torch.log(scale) - 0.5 * np.log(2 * np.pi)
+            - 2.0 * (np.log(2.0) - raw - F.softplus(-2.0 * raw))).sum(-1)
+    return torch.tanh(raw), dict(raw_action=raw, log_prob=logp, logits=logits, latent_mean=mean, latent_logvar=logvar)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from track_mjx_b200.policy import IntentionNetworkConfig, IntentionPolicy, init_params
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = IntentionNetworkConfig()
+    p = init_params(cfg, seed=0)
+    rng = np.random.default_rng(1)
+    # non-trivial normaliser, biases and LayerNorm affine so that every parameter is exercised
+    p["norm/mean"] = rng.normal(0, 0.1, cfg.obs_size).astype(np.float32)
+    p["norm/std"] = rng.uniform(0.5, 2.0, cfg.obs_size).astype(np.float32)
+    for k in list(p):
+        if k.endswith("/bias"):
+            p[k] = rng.normal(0, 0.05, p[k].shape).astype(np.float32)
+        if k.endswith("/scale"):
+            p[k] = rng.uniform(0.8, 1.2, p[k].shape).astype(np.float32)
+    pol = IntentionPolicy(cfg, p, max_env=1000)
+    yield cfg, p, pol
+    pol.close()
+
+
+@pytest.mark.parametrize("which,n", [(0, 1000), (1, 128), (5, 77), (6, 300), (11, 129)])
+def test_single_layer_matches_fp32(setup, which, n):
+    cfg, p, pol = setup
+    dev = pol.device
+    enc = list(cfg.encoder_layers)
+    dec = list(cfg.decoder_layers)
+    ins = [cfg.reference_obs_size] + enc[:-1] + [enc[-1]] + [cfg.latent_size + cfg.obs_size - cfg.reference_obs_size] + dec
+    outs = enc + [2 * cfg.latent_size] + dec + [2 * cfg.action_size]
+    k, no = ins[which], outs[which]
+    kpad, npad = (k + 31) // 32 * 32, (no + 127) // 128 * 128
+    g = torch.Generator(device="cpu").manual_seed(which)
+    x = torch.zeros(n, kpad, device=dev)
+    x[:, :k] = torch.randn(n, k, generator=g).to(dev)
+    y = torch.full((n, npad), float("nan"), device=dev)
+    pol.linear(which, x, y)
+    torch.cuda.synchronize()
+    t = lambda key: torch.from_numpy(p[key]).to(dev)
+    ne = len(enc)
+    if which < ne:
+        name, ln = f"encoder/hidden_{which}", f"encoder/LayerNorm_{which}"
+    elif which == ne:
+        name, ln = None, None
+    else:
+        i = which - ne - 1
+        name, ln = f"decoder/hidden_{i}", (f"decoder/LayerNorm_{i}" if i < len(dec) else None)
+    if name is None:
+        W = torch.cat([t("encoder/fc2_mean/kernel"), t("encoder/fc2_logvar/kernel")], 1)
+        b = torch.cat([t("encoder/fc2_mean/bias"), t("encoder/fc2_logvar/bias")])
+    else:
+        W, b = t(name + "/kernel"), t(name + "/bias")
+    ref = x[:, :k] @ W + b
+    if ln is not None:
+        ref = torch.nn.functional.layer_norm(torch.nn.functional.silu(ref), (no,), t(ln + "/scale"), t(ln + "/bias"), eps=1e-6)
+    err = (y[:, :no] - ref).abs().max().item()
+    assert torch.isfinite(y[:, :no]).all()
+    assert err < 4e-3, err
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_act_matches_fp32_reference(setup, deterministic):
+    cfg, p, pol = setup
+    n = 777
+    g = torch.Generator(device="cpu").manual_seed(5)
+    obs = torch.randn(n, cfg.obs_size, generator=g).to(pol.device)
+    ez = torch.randn(n, cfg.latent_size, generator=g).to(pol.device)
+    ea = torch.randn(n, cfg.action_size, generator=g).to(pol.device)
+    act, ex = pol.act(obs, ez, ea, deterministic=deterministic)
+    torch.cuda.synchronize()
+    ract, rex = torch_reference(cfg, p, obs, ez, ea, deterministic)
+    assert (ex["latent_mean"] - rex["latent_mean"]).abs().max().item() < 2e-2
+    assert (ex["latent_logvar"] - rex["latent_logvar"]).abs().max().item() < 2e-2
+    assert (ex["logits"] - rex["logits"]).abs().max().item() < 2e-2
+    assert (act - ract).abs().max().item() < 2e-2
+    # log_prob evaluated at the kernel's own sample must agree with the closed form on the kernel's logits (fp32 path)
+    loc, rs = ex["logits"][:, : cfg.action_size], ex["logits"][:, cfg.action_size:]
+    scale = torch.nn.functional.softplus(rs) + 0.001
+    raw = ex["raw_action"]
+    lp = (-0.5 * ((raw - loc) / scale) ** 2 - torch.log(scale) - 0.5 * np.log(2 * np.pi)
+          - 2.0 * (np.log(2.0) - raw - torch.nn.functional.softplus(-2.0 * raw))).sum(-1)
+    assert (ex["log_prob"] - lp).abs().max().item() < 1e-3 * max(1.0, lp.abs().max().item())
+    assert (act.abs() <= 1).all()

@@ -48,6 +48,12 @@ class OutC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n, _, _ in OUT_FIELDS + DEBUG_FIELDS]
 
 
+class PolicyDescC(C.Structure):
+    _fields_ = [("obs_size", C.c_int32), ("reference_obs_size", C.c_int32), ("latent_size", C.c_int32), ("action_size", C.c_int32),
+                ("n_encoder_layers", C.c_int32), ("encoder_layers", C.c_int32 * 8),
+                ("n_decoder_layers", C.c_int32), ("decoder_layers", C.c_int32 * 8)]
+
+
 class DimsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "nq", "nv", "nu", "na", "nbody", "njnt", "ncon", "nefc", "obs_size", "reference_obs_size",
@@ -106,6 +112,15 @@ def load() -> C.CDLL:
     lib.tmjx_step.argtypes = [vp, vp, vp, C.POINTER(StateC), C.POINTER(OutC), i32, u32, vp]
     lib.tmjx_fp32_peak_tflops.argtypes = [i32, vp]
     lib.tmjx_fp32_peak_tflops.restype = C.c_double
+    lib.tmjx_policy_param_count.argtypes = [C.POINTER(PolicyDescC)]
+    lib.tmjx_policy_param_count.restype = sz
+    lib.tmjx_policy_create.argtypes = [C.POINTER(PolicyDescC), fp, sz, i32, i32, C.POINTER(vp)]
+    lib.tmjx_policy_destroy.argtypes = [vp]
+    lib.tmjx_policy_destroy.restype = None
+    lib.tmjx_policy_last_error.restype = C.c_char_p
+    lib.tmjx_policy_act.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.tmjx_policy_linear.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp]
+    lib.tmjx_policy_launches_per_act.argtypes = [vp]
     if lib.tmjx_abi_version() != 1:
         raise ImportError("libtmjx.so ABI version mismatch")
     _lib = lib

@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's intention-network acting policy, driving the tcgen05 kernels in csrc/tmjx_policy.cu.
+
+Reference: `track_mjx/agent/mlp_ppo/intention_network.py:14-142` (Encoder / Decoder / IntentionNetwork),
+`ppo_networks.py:34-100` (make_inference_fn: sample, log_prob, postprocess), `masked_running_statistics.py:217-236`
+(normalize).  Parameters are held as a dict that mirrors the flax tree (`encoder/hidden_i/{kernel,bias}`,
+`encoder/LayerNorm_i/{scale,bias}`, `encoder/fc2_mean`, `encoder/fc2_logvar`, `decoder/...`); `flatten_params` lays them out in
+the order include/tmjx.h documents.  Inference only: there is no CPU fallback and no autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class IntentionNetworkConfig:
+    """network_config of config/rodent-full-clips.yaml:50-57 plus the env's observation sizes."""
+    obs_size: int = 696
+    reference_obs_size: int = 470
+    action_size: int = 38
+    latent_size: int = 60
+    encoder_layers: Sequence[int] = (1024, 512, 512, 512, 512)
+    decoder_layers: Sequence[int] = (512, 512, 512, 256, 256)
+
+
+def init_params(cfg: IntentionNetworkConfig, seed: int = 0) -> Dict[str, np.ndarray]:
+    """LeCun-uniform kernels (flax Dense default in the reference: `jax.nn.initializers.lecun_uniform()`), zero biases,
+    LayerNorm scale 1 / bias 0, identity normaliser.  numpy RNG: stream parity with jax.random is not claimed."""
+    rng = np.random.default_rng(seed)
+    p: Dict[str, np.ndarray] = {"norm/mean": np.zeros(cfg.obs_size, np.float32), "norm/std": np.ones(cfg.obs_size, np.float32)}
+
+    def dense(name, k, n):
+        lim = np.sqrt(3.0 / k)
+        p[f"{name}/kernel"] = rng.uniform(-lim, lim, size=(k, n)).astype(np.float32)
+        p[f"{name}/bias"] = np.zeros(n, np.float32)
+
+    k = cfg.reference_obs_size
+    for i, n in enumerate(cfg.encoder_layers):
+        dense(f"encoder/hidden_{i}", k, n)
+        p[f"encoder/LayerNorm_{i}/scale"] = np.ones(n, np.float32)
+        p[f"encoder/LayerNorm_{i}/bias"] = np.zeros(n, np.float32)
+        k = n
+    dense("encoder/fc2_mean", k, cfg.latent_size)
+    dense("encoder/fc2_logvar", k, cfg.latent_size)
+    k = cfg.latent_size + cfg.obs_size - cfg.reference_obs_size
+    for i, n in enumerate(cfg.decoder_layers):
+        dense(f"decoder/hidden_{i}", k, n)
+        p[f"decoder/LayerNorm_{i}/scale"] = np.ones(n, np.float32)
+        p[f"decoder/LayerNorm_{i}/bias"] = np.zeros(n, np.float32)
+        k = n
+    dense(f"decoder/hidden_{len(cfg.decoder_layers)}", k, 2 * cfg.action_size)
+    return p
+
+
+def flatten_params(cfg: IntentionNetworkConfig, p: Dict[str, np.ndarray]) -> np.ndarray:
+    parts = [p["norm/mean"], p["norm/std"]]
+    for i in range(len(cfg.encoder_layers)):
+        parts += [p[f"encoder/hidden_{i}/kernel"], p[f"encoder/hidden_{i}/bias"], p[f"encoder/LayerNorm_{i}/scale"], p[f"encoder/LayerNorm_{i}/bias"]]
+    parts += [p["encoder/fc2_mean/kernel"], p["encoder/fc2_mean/bias"], p["encoder/fc2_logvar/kernel"], p["encoder/fc2_logvar/bias"]]
+    for i in range(len(cfg.decoder_layers)):
+        parts += [p[f"decoder/hidden_{i}/kernel"], p[f"decoder/hidden_{i}/bias"], p[f"decoder/LayerNorm_{i}/scale"], p[f"decoder/LayerNorm_{i}/bias"]]
+    n = len(cfg.decoder_layers)
+    parts += [p[f"decoder/hidden_{n}/kernel"], p[f"decoder/hidden_{n}/bias"]]
+    return np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32).ravel() for a in parts]))
+
+
+def make_desc(cfg: IntentionNetworkConfig) -> L.PolicyDescC:
+    d = L.PolicyDescC()
+    d.obs_size, d.reference_obs_size, d.latent_size, d.action_size = cfg.obs_size, cfg.reference_obs_size, cfg.latent_size, cfg.action_size
+    d.n_encoder_layers = len(cfg.encoder_layers)
+    d.n_decoder_layers = len(cfg.decoder_layers)
+    for i, n in enumerate(cfg.encoder_layers):
+        d.encoder_layers[i] = int(n)
+    for i, n in enumerate(cfg.decoder_layers):
+        d.decoder_layers[i] = int(n)
+    return d
+
+
+class IntentionPolicy:
+    """`policy(observations, key) -> (action, extras)` of make_inference_fn on the GPU.  Torch is plumbing only (device
+    buffers and the Gaussian noise the reference draws with jax.random)."""
+
+    def __init__(self, cfg: IntentionNetworkConfig, params: Dict[str, np.ndarray], max_env: int, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("IntentionPolicy needs a CUDA device: there is no CPU fallback")
+        self.torch = torch
+        self.cfg, self.max_env = cfg, int(max_env)
+        self.device = torch.device("cuda", device)
+        self.lib = L.load()
+        flat = flatten_params(cfg, params)
+        desc = make_desc(cfg)
+        if flat.size != self.lib.tmjx_policy_param_count(C.byref(desc)):
+            raise ValueError("parameter tree does not match the network config")
+        self._p = C.c_void_p()
+        rc = self.lib.tmjx_policy_create(C.byref(desc), flat.ctypes.data_as(C.POINTER(C.c_float)), flat.size, device, self.max_env, C.byref(self._p))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_policy_create failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+        f = dict(dtype=torch.float32, device=self.device)
+        n, a, z = self.max_env, cfg.action_size, cfg.latent_size
+        self.out = {"action": torch.empty(n, a, **f), "raw_action": torch.empty(n, a, **f), "log_prob": torch.empty(n, **f),
+                    "logits": torch.empty(n, 2 * a, **f), "latent_mean": torch.empty(n, z, **f), "latent_logvar": torch.empty(n, z, **f)}
+        self.launches_per_act = int(self.lib.tmjx_policy_launches_per_act(self._p))
+
+    def act(self, obs, eps_latent=None, eps_action=None, deterministic: bool = False):
+        """obs: [n, obs_size] CUDA tensor.  Returns (action, extras) views into buffers owned by the policy."""
+        t = self.torch
+        n = int(obs.shape[0])
+        if not deterministic:
+            if eps_latent is None:
+                eps_latent = t.randn(n, self.cfg.latent_size, device=self.device)
+            if eps_action is None:
+                eps_action = t.randn(n, self.cfg.action_size, device=self.device)
+        ptr = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        o = self.out
+        rc = self.lib.tmjx_policy_act(self._p, ptr(obs), ptr(eps_latent), ptr(eps_action), int(deterministic), ptr(o["action"]),
+                                      ptr(o["raw_action"]), ptr(o["log_prob"]), ptr(o["logits"]), ptr(o["latent_mean"]),
+                                      ptr(o["latent_logvar"]), n, C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_policy_act failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+        return o["action"][:n], {k: v[:n] for k, v in o.items() if k != "action"}
+
+    def linear(self, which: int, x, y):
+        rc = self.lib.tmjx_policy_linear(self._p, which, C.c_void_p(x.data_ptr()), int(x.stride(0)), C.c_void_p(y.data_ptr()), int(y.stride(0)),
+                                         int(x.shape[0]), C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_policy_linear failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+
+    def close(self):
+        if self._p:
+            self.lib.tmjx_policy_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
