@@ -32,17 +32,37 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "rodent-tracking env-steps/sec (device-timed)"
 UNIT = "env-steps/s"
 ENVS_PER_GPU = 4096
+# BASELINE.json configs: the default bench line is configs[1]; the others are selectable parity / scaling cases
+WORKLOADS = {
+    "tracking": dict(envs=4096, n_clips=1, policy=False, env_args={}, w_alg=None,
+                     name="rodent single-clip tracking, 4096 envs per B200, full step + reward + obs + fused auto-reset, fp32 (BASELINE configs[1])"),
+    "intention": dict(envs=16384, n_clips=842, policy=True, env_args={}, w_alg=None,
+                      name="rodent-mc-intention multi-clip, 842 synthetic clips, 16384 envs per B200, in-loop intention-network policy "
+                           "inference on tcgen05 (tf32) + full step (BASELINE configs[2])"),
+    "contact": dict(envs=4096, n_clips=1, policy=False,
+                    env_args=dict(solver="newton", iterations=10, ls_iterations=10, physics_steps_per_control_step=20), w_alg=None,
+                    name="contact-heavy rodent tracking: Newton solver, 10 iterations / 10 line-search iterations, 20 physics steps per "
+                         "control step, 4096 envs per B200 (BASELINE configs[4], 32768 envs on 8 GPUs)"),
+}
 # algorithmic work per env-step at the default config (formulas in DESIGN.md "Roofline")
 B_ALG = 15348.0            # bytes of unavoidable HBM traffic per env-step
 W_ALG = 3.775e6            # structure-exploiting FLOPs per env-step (10 x 375 kFLOP + 25 kFLOP)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, workload="tracking"):
+    from track_mjx_b200 import config
+
+    w = WORKLOADS[workload]
+    ea = dict(config.DEFAULT_ENV_ARGS)
+    ea.update(w["env_args"])
     return {
-        "workload": "rodent single-clip tracking, 4096 envs per B200, full step + reward + obs + fused auto-reset, fp32 (BASELINE configs[1])",
-        "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus, "n_clips": 1, "clip_length": 250,
-        "physics_steps_per_control_step": 10, "solver": "cg", "iterations": 5, "ls_iterations": 5,
-        "actions": "N(0,1) per step (clipped to ctrlrange by the actuator model)", "l2": "flushed between timed iterations",
+        "workload": w["name"],
+        "envs_per_gpu": w["envs"], "global_envs": w["envs"] * n_gpus, "n_clips": w["n_clips"], "clip_length": 250,
+        "physics_steps_per_control_step": ea["physics_steps_per_control_step"], "solver": ea["solver"], "iterations": ea["iterations"],
+        "ls_iterations": ea["ls_iterations"],
+        "actions": ("tanh-normal samples of the seed-0 LeCun-uniform intention network on the env's own observations" if w["policy"]
+                    else "N(0,1) per step (clipped to ctrlrange by the actuator model)"),
+        "l2": "flushed between timed iterations",
         "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
     }
 
@@ -145,7 +165,9 @@ def run_ours(args, rank, world, local_rank):
     from track_mjx_b200.env import MultiClipTracking, wrap
     from track_mjx_b200.sharding import Shard, max_over_ranks, reduce_episode_stats
 
-    shard = Shard(rank, world, ENVS_PER_GPU * world)   # weak scaling: 4096 envs per GPU, contiguous global env ids per rank
+    wl = WORKLOADS[args.workload]
+    ENVS_PER_GPU = wl["envs"]
+    shard = Shard(rank, world, ENVS_PER_GPU * world)   # weak scaling: fixed envs per GPU, contiguous global env ids per rank
     dist = None
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
@@ -156,14 +178,34 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    walker, clips, config = build_env_pieces(1)
-    env = wrap(MultiClipTracking(clips, walker, config.RewardConfig(), num_envs=ENVS_PER_GPU, device=local_rank, **config.DEFAULT_ENV_ARGS))
+    walker, clips, config = build_env_pieces(wl["n_clips"])
+    env_args = dict(config.DEFAULT_ENV_ARGS)
+    env_args.update(wl["env_args"])
+    env = wrap(MultiClipTracking(clips, walker, config.RewardConfig(), num_envs=ENVS_PER_GPU, device=local_rank, **env_args))
     state = env.reset(shard.seed(1000))
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
     n_act = min(K + W, 64)
-    acts = [torch.randn(ENVS_PER_GPU, env.action_size, device=dev, generator=gen) for _ in range(n_act)]
+    policy = None
+    if wl["policy"]:
+        from track_mjx_b200.policy import IntentionNetworkConfig, IntentionPolicy, init_params
+
+        pcfg = IntentionNetworkConfig(obs_size=env.observation_size, reference_obs_size=env.stepper.dims["reference_obs_size"],
+                                      action_size=env.action_size)
+        policy = IntentionPolicy(pcfg, init_params(pcfg, seed=0), max_env=ENVS_PER_GPU, device=local_rank)
+        eps = [(torch.randn(ENVS_PER_GPU, pcfg.latent_size, device=dev, generator=gen),
+                torch.randn(ENVS_PER_GPU, pcfg.action_size, device=dev, generator=gen)) for _ in range(min(n_act, 8))]
+        acts = None
+    else:
+        acts = [torch.randn(ENVS_PER_GPU, env.action_size, device=dev, generator=gen) for _ in range(n_act)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def next_action(i, st):
+        """random actions, or the in-loop policy on the current observations (acting half of ppo.py:333-340)"""
+        if policy is None:
+            return acts[i % n_act]
+        ez, ea = eps[i % len(eps)]
+        return policy.act(st.obs, ez, ea)[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -172,12 +214,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident arm
     for i in range(W):
-        state = env.step(state, acts[i % n_act])
+        state = env.step(state, next_action(i, state))
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(K)]
     barrier()
     wall0 = time.perf_counter()
     rew_sum = torch.zeros((), device=dev)
@@ -185,13 +227,17 @@ def run_ours(args, rank, world, local_rank):
     for i in range(K):
         flush.zero_()
         evs[i][0].record()
-        state = env.step(state, acts[(W + i) % n_act])
+        a_i = next_action(W + i, state)
         evs[i][1].record()
+        state = env.step(state, a_i)
+        evs[i][2].record()
         rew_sum += state.reward.sum()
         done_sum += state.done.sum()
     barrier()
     wall = time.perf_counter() - wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = sum(a.elapsed_time(c) for a, _, c in evs)
+    kern_ms = sum(b.elapsed_time(c) for _, b, c in evs)      # the step kernel alone
+    pol_ms = sum(a.elapsed_time(b) for a, b, _ in evs)       # the policy kernels (0 launches for random actions)
     clocks = sampler.stop() if rank == 0 else None
     max_ms = max_over_ranks(dev_ms, dev, shard)                      # device time, max over ranks
     stats = reduce_episode_stats(rew_sum, done_sum, K, shard)        # SUM over NVLink: the only collective of the env path
@@ -201,13 +247,24 @@ def run_ours(args, rank, world, local_rank):
     obs_dim = env.observation_size
     h_act = [torch.randn(ENVS_PER_GPU, env.action_size).pin_memory() for _ in range(4)]
     d_act = torch.empty(ENVS_PER_GPU, env.action_size, device=dev)
+    if policy is not None:
+        h_ez = [torch.randn(ENVS_PER_GPU, pcfg.latent_size).pin_memory() for _ in range(4)]
+        h_ea = [torch.randn(ENVS_PER_GPU, pcfg.action_size).pin_memory() for _ in range(4)]
+        d_ez = torch.empty(ENVS_PER_GPU, pcfg.latent_size, device=dev)
+        d_ea = torch.empty(ENVS_PER_GPU, pcfg.action_size, device=dev)
     h_obs = torch.empty(ENVS_PER_GPU, obs_dim).pin_memory()
     h_rew = torch.empty(ENVS_PER_GPU).pin_memory()
     h_done = torch.empty(ENVS_PER_GPU).pin_memory()
 
     def e2e_step(i, st):
-        d_act.copy_(h_act[i % 4], non_blocking=True)
-        st = env.step(st, d_act)
+        if policy is None:
+            d_act.copy_(h_act[i % 4], non_blocking=True)
+            a = d_act
+        else:   # the policy consumes the device-resident observation; its Gaussian noise comes from pinned host memory
+            d_ez.copy_(h_ez[i % 4], non_blocking=True)
+            d_ea.copy_(h_ea[i % 4], non_blocking=True)
+            a = policy.act(st.obs, d_ez, d_ea)[0]
+        st = env.step(st, a)
         h_obs.copy_(st.obs, non_blocking=True)
         h_rew.copy_(st.reward, non_blocking=True)
         h_done.copy_(st.done, non_blocking=True)
@@ -223,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_value = ENVS_PER_GPU * world * K / max_over_ranks(e2e_s, dev, shard)
-    h2d = ENVS_PER_GPU * env.action_size * 4
+    h2d = ENVS_PER_GPU * (env.action_size if policy is None else pcfg.latent_size + pcfg.action_size) * 4
     d2h = ENVS_PER_GPU * (obs_dim + 2) * 4
 
     if rank != 0:
@@ -239,31 +296,41 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     fp32_peak = env.stepper.fp32_peak_tflops()   # FMA microbenchmark on this box (no fp32 figure in MEASURED_PEAKS.json)
-    per_gpu_rate = ENVS_PER_GPU * K / (max_ms * 1e-3)
+    kern_rate = ENVS_PER_GPU * K / (kern_ms * 1e-3)   # env-steps/s of the step kernel on rank 0
+    per_gpu_rate = kern_rate
+    nf, its = env_args["physics_steps_per_control_step"], env_args["iterations"]
+    # canonical FLOPs per env-step: per substep 205 kFLOP outside the solver + 34 kFLOP per CG iteration; Newton adds
+    # the Hessian assembly + one sparse factorisation per iteration (~2 x 21 kFLOP + 25 kFLOP)
+    w_sub = 205e3 + its * (34e3 + (67e3 if env_args["solver"] == "newton" else 0.0))
+    W_ALG_WL = nf * w_sub + 25e3
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "step_kernel_dram_bytes.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {
-        "bound": "fp32", "achieved": per_gpu_rate * W_ALG / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": per_gpu_rate * W_ALG / 1e12 / fp32_peak if fp32_peak > 0 else None, "traffic": traffic,
+        "bound": "fp32", "achieved": per_gpu_rate * W_ALG_WL / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": per_gpu_rate * W_ALG_WL / 1e12 / fp32_peak if fp32_peak > 0 else None, "traffic": traffic if args.workload == "tracking" else None,
         "peak_source": "measured FP32 FMA microbenchmark (tmjx_fp32_peak_tflops) in this run",
-        "kernel": "tmjx_env_kernel<true>", "kernel_ms": max_ms / K, "algorithmic_flops_per_launch": W_ALG * ENVS_PER_GPU,
+        "kernel": "tmjx_env_kernel<true>", "kernel_ms": kern_ms / K, "algorithmic_flops_per_launch": W_ALG_WL * ENVS_PER_GPU,
         "algorithmic_bytes_per_launch": B_ALG * ENVS_PER_GPU,
         "hbm": {"achieved": per_gpu_rate * B_ALG / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu_rate * B_ALG / 1e9 / hbm_peak,
                 "peak_source": hbm_src},
     }
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "tracking":
         cpu_baseline = cpu_baseline_leg(walker, clips, config)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world), "clocks": clocks, "gpu_launches": K,
+        "config": workload_config(world, args.workload), "clocks": clocks,
+        "gpu_launches": K * (1 + (policy.launches_per_act if policy is not None else 0)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "policy": None if policy is None else {
+            "ms_per_step": pol_ms / K, "launches_per_step": policy.launches_per_act, "kernel": "linear_tf32_kernel (tcgen05 kind::tf32) + row kernels",
+            "flops_per_env_step": 5.48e6, "achieved_tflops": 5.48e6 * ENVS_PER_GPU * K / (pol_ms * 1e-3) / 1e12},
         "wall_s_timed_region": wall,
         "episode_stats": stats,
     }
@@ -303,10 +370,12 @@ def cpu_baseline_leg(walker, clips, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tracking", choices=sorted(WORKLOADS),
+                    help="tracking = BASELINE configs[1] (the bench line); intention = configs[2]; contact = configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
