@@ -83,3 +83,42 @@ def test_synthetic_clip_shapes(walker, clips2):
     assert np.allclose(c.body_positions[:, :, 0], 0) and np.allclose(c.body_positions[:, :, 1], c.position, atol=1e-6)
     again = clipmod.make_synthetic_clips(walker.sections, 2)
     assert (again.joints == c.joints).all()
+
+
+def test_policy_param_layout_matches_c_count():
+    """The flattened parameter vector (policy.flatten_params) has exactly the length the C side derives from the descriptor
+    (include/tmjx.h, tmjx_policy_param_count), for the reference network (rodent-full-clips.yaml:50-57) and a small one."""
+    from track_mjx_b200 import policy as P
+
+    lib = L.load()
+    for cfg in (P.IntentionNetworkConfig(), P.IntentionNetworkConfig(obs_size=40, reference_obs_size=24, action_size=3, latent_size=4,
+                                                                        encoder_layers=(16, 8), decoder_layers=(8,))):
+        p = P.init_params(cfg, seed=0)
+        flat = P.flatten_params(cfg, p)
+        desc = P.make_desc(cfg)
+        assert flat.dtype == np.float32 and flat.size == lib.tmjx_policy_param_count(C.byref(desc))
+        # LeCun-uniform bound of the first kernel: sqrt(3 / fan_in)
+        k0 = p["encoder/hidden_0/kernel"]
+        assert k0.shape == (cfg.reference_obs_size, cfg.encoder_layers[0]) and np.abs(k0).max() <= np.sqrt(3.0 / cfg.reference_obs_size)
+    full = P.IntentionNetworkConfig()
+    macs = 0
+    k = full.reference_obs_size
+    for n in full.encoder_layers:
+        macs += k * n
+        k = n
+    macs += k * 2 * full.latent_size
+    k = full.latent_size + full.obs_size - full.reference_obs_size
+    for n in list(full.decoder_layers) + [2 * full.action_size]:
+        macs += k * n
+        k = n
+    assert abs(2 * macs - 5.48e6) < 0.02e6          # the 5.5 MFLOP / env-step of SURVEY 8f
+
+
+def test_policy_struct_layout_matches_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "tmjx.h"\nint main(){printf("%zu %zu\\n", sizeof(TmjxPolicyDesc), '
+                   '__builtin_offsetof(TmjxPolicyDesc, n_decoder_layers));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(L.PolicyDescC), L.PolicyDescC.n_decoder_layers.offset]
