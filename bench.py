@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference (JAX/MJX/Brax) not installable in this image; this is the CPU oracle port of its algorithm",
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -334,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         "wall_s_timed_region": wall,
         "episode_stats": stats,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -367,7 +367,24 @@ def cpu_baseline_leg(walker, clips, config):
             "sample": f"{sample} of {ENVS_PER_GPU} envs x {steps} control steps, fp32 CPU oracle (port of the MJX algorithm, dense), OpenMP over envs"}
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The one JSON line goes to the REAL stdout; everything else a library prints there (NCCL's version banner is written
+    straight to fd 1 by the C library) has been routed to stderr by main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
