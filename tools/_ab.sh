@@ -4,7 +4,6 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; e
 tail -15 $OUT/${TAG}_pytest.log
 (
   timeout 300 python tools/gpu_perf_sweep.py 4096 8192
-  TMJX_SYNC=-1 timeout 300 python tools/gpu_perf_sweep.py 4096
-  TMJX_SYNC=1 timeout 300 python tools/gpu_perf_sweep.py 4096
 ) > $OUT/${TAG}_sweep.log 2>&1
 cat $OUT/${TAG}_sweep.log
+timeout 600 python bench.py --workload contact --steps 10 --warmup 3 2>/dev/null | cut -c1-160

@@ -438,10 +438,12 @@ def emit_cuda(t: Tree) -> str:
     w("}")
     w("// Both L^T D L factorisations (M at L, M + dt diag(damping) at L + kNMpad), stacked half-warp per matrix; see")
     w("// factor_dual in tmjx_step.cu for the loop form of the same schedule (used for other trees).")
-    w("static __device__ __noinline__ void factor_dual(float* __restrict__ L, int lane, bool sync) {")
+    w("// off2 = kNMpad: two matrices; off2 = 0: both half-warps factor the SAME matrix at L (identical values, identical stores)")
+    w("// -- the single-matrix factorisation Newton needs once per solver iteration, at the same instruction count.")
+    w("static __device__ __noinline__ void factor_dual(float* __restrict__ L, int lane, bool sync, int off2) {")
     w("  const unsigned lb = 1u << lane;")
     w("  const int hbit = lane & 16;")
-    w("  float* ps = L + (hbit ? kNMpad : 0) - (lane & 15);")
+    w("  float* ps = L + (hbit ? off2 : 0) - (lane & 15);")
     fir = build_factor_ir(t)
     w("  float w0 = 0.f, w1 = 0.f, w2 = 0.f, d, inv, a;")
     declared = set()

@@ -708,7 +708,7 @@ __device__ void build_m(const Warp& w) {
       const float vd = L1[e] + m.dof_armature[d];
       L1[e] = vd;
       L2[e] = vd + __fmul_rn(m.dt, m.dof_damping[d]);
-      if (m.o_L != m.o_big) w.at(m.o_L)[e] = vd;
+      if (m.o_L != m.o_big) w.at(m.o_L)[e] = vd;   // Newton
     }
   }
   __syncwarp();
@@ -1265,7 +1265,15 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   const DevModel& m = w.m;
   float* sx = w.at(m.o_cin + m.c_sx);
   const float* L1 = w.at(m.o_L);
+  // the residency variants are solver-specialised: 14 warps = CG only, 10 warps = Newton only (its slice carries a third
+  // matrix), 4 warps = either (runtime); dropping the other solver's code shrinks the hot kernel's instruction footprint
+#if TMJX_VARIANT == 14
+  constexpr bool newton = false;
+#elif TMJX_VARIANT == 10
+  constexpr bool newton = true;
+#else
   const bool newton = m.solver == TMJX_SOLVER_NEWTON;
+#endif
   float warm[kNvSlots];
   vget(w, w.at(m.o_warm), warm);
 
@@ -1320,7 +1328,8 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) Mgrad[q] = grad[q];
     if (newton) {  // H = M + J^T diag(D active) J, assembled and factored in the o_L block (same tree sparsity as M)
       build_hessian(w, r, Jaref);
-      factor_single(w, w.at(m.o_L));
+      if (m.use_gen) { __syncwarp(); gen::factor_dual(w.at(m.o_L), w.lane, false, 0); __syncwarp(); }
+      else factor_single(w, w.at(m.o_L));
     }
     solve_ld(w, L1, Mgrad);
   };
@@ -1470,7 +1479,7 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
     mul_m_raw(w, w.at(m.o_warm), Maw);
   }
   __syncwarp();
-  if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1); __syncwarp(); } else factor_dual(w);
+  if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1, gen::kNMpad); __syncwarp(); } else factor_dual(w);
   if (m.sync_level > 0) phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
@@ -1999,7 +2008,8 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   // One block per SM with all of its warps in lock-step (phase_sync): 14 resident environments per SM when the per-env
   // slice allows it (CG), 10 for larger slices (Newton keeps a third sparse matrix), else blocks of 4.
   const size_t optin = prop.sharedMemPerBlockOptin;
-  m->envs_per_block = per_env * 14 <= optin ? 14 : (per_env * 10 <= optin ? 10 : 4);
+  const bool is_newton = m->dm.solver == TMJX_SOLVER_NEWTON;
+  m->envs_per_block = (!is_newton && per_env * 14 <= optin) ? 14 : ((is_newton && per_env * 10 <= optin) ? 10 : 4);
   if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
