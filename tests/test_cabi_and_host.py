@@ -122,3 +122,24 @@ def test_policy_struct_layout_matches_c(tmp_path):
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(L.PolicyDescC), L.PolicyDescC.n_decoder_layers.offset]
+
+
+def test_multiclip_loader_round_trip(walker, tmp_path):
+    """make_multiclip_data (reference io/load.py:105-137) on stac-mjx-shaped flat arrays reproduces the clip table field by
+    field, from a mapping and from an .npz; select_clips / generate_train_test_split partition the clips (load.py:187-278)."""
+    clips = clipmod.make_synthetic_clips(walker.sections, 5, clip_length=60)
+    flat = clipmod.to_stac_arrays(clips)
+    assert flat["qpos"].shape == (300, 74) and flat["qvel"].shape == (300, 73) and flat["xpos"].shape == (300, 67, 3)
+    again = clipmod.make_multiclip_data(flat, n_frames_per_clip=60)
+    np.savez(tmp_path / "clips.npz", n_frames_per_clip=60, **flat)
+    from_file = clipmod.make_multiclip_data(str(tmp_path / "clips.npz"))
+    for k in ("position", "quaternion", "joints", "body_positions", "velocity", "angular_velocity", "joints_velocity", "body_quaternions"):
+        assert np.array_equal(getattr(again, k), np.asarray(getattr(clips, k), np.float32)), k
+        assert np.array_equal(getattr(from_file, k), getattr(again, k)), k
+    with pytest.raises(ValueError):
+        clipmod.make_multiclip_data(flat, n_frames_per_clip=70)
+    train, test = clipmod.generate_train_test_split(again, test_ratio=0.4, rng=np.random.default_rng(0))
+    assert train.n_clips == 3 and test.n_clips == 2
+    both = np.sort(np.concatenate([train.original_clip_idx[:, 0], test.original_clip_idx[:, 0]]))
+    assert np.array_equal(both, np.arange(5))
+    assert np.array_equal(test.joints, again.joints[test.original_clip_idx[:, 0]])

@@ -123,3 +123,44 @@ def test_act_matches_fp32_reference(setup, deterministic):
           - 2.0 * (np.log(2.0) - raw - torch.nn.functional.softplus(-2.0 * raw))).sum(-1)
     assert (ex["log_prob"] - lp).abs().max().item() < 1e-3 * max(1.0, lp.abs().max().item())
     assert (act.abs() <= 1).all()
+
+
+def test_zero_copy_rollout_matches_step_by_step(walker, clips2):
+    """Rollout.generate (obs written by the step kernel straight into the [T+1, B, obs] buffer, policy outputs into slot t)
+    equals acting step by step through env.step / policy.act on the same noise -- bit for bit (deterministic kernels)."""
+    from track_mjx_b200 import config
+    from track_mjx_b200.env import MultiClipTracking, wrap
+    from track_mjx_b200.policy import IntentionNetworkConfig, IntentionPolicy, init_params
+    from track_mjx_b200.rollout import Rollout
+
+    n, T = 96, 5
+    pcfg = IntentionNetworkConfig()
+    params = init_params(pcfg, seed=3)
+
+    def make():
+        env = wrap(MultiClipTracking(clips2, walker, config.RewardConfig(), num_envs=n, device=0, **config.DEFAULT_ENV_ARGS))
+        return env, env.reset(7), IntentionPolicy(pcfg, params, max_env=n)
+
+    g = torch.Generator(device="cpu").manual_seed(11)
+    ez = torch.randn(T, n, pcfg.latent_size, generator=g).cuda()
+    ea = torch.randn(T, n, pcfg.action_size, generator=g).cuda()
+
+    env, st, pol = make()
+    ro = Rollout(env, pol, T)
+    st_end, tr = ro.generate(st, eps=(ez, ea))
+    torch.cuda.synchronize()
+
+    env2, st2, pol2 = make()
+    obs_seq, rew_seq, done_seq, act_seq = [st2.obs.clone()], [], [], []
+    for t in range(T):
+        a, _ = pol2.act(st2.obs, ez[t], ea[t])
+        act_seq.append(a.clone())
+        st2 = env2.step(st2, a)
+        obs_seq.append(st2.obs.clone()); rew_seq.append(st2.reward.clone()); done_seq.append(st2.done.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(tr.observation, torch.stack(obs_seq[:-1])) and torch.equal(tr.next_observation, torch.stack(obs_seq[1:]))
+    assert torch.equal(tr.action, torch.stack(act_seq))
+    assert torch.equal(tr.reward, torch.stack(rew_seq)) and torch.equal(1.0 - tr.discount, torch.stack(done_seq))
+    assert torch.equal(st_end.obs, st2.obs) and torch.equal(st_end.pipeline_state.qpos, st2.pipeline_state.qpos)
+    assert tr.extras["state_extras"]["truncation"].shape == (T, n)
+    assert torch.isfinite(tr.extras["policy_extras"]["log_prob"]).all()

@@ -148,3 +148,74 @@ def make_synthetic_clips(sec: dict[str, np.ndarray], n_clips: int, clip_length: 
         body_positions=xpos.astype(f32), velocity=qvel[..., :3].astype(f32),
         angular_velocity=qvel[..., 3:6].astype(f32), joints_velocity=qvel[..., 6:].astype(f32),
         body_quaternions=xquat.astype(f32), original_clip_idx=np.arange(n_clips, dtype=np.int32))
+
+
+# --------------------------------------------------------------------------- stac-mjx data -> clip table
+_FIELDS = ("position", "quaternion", "joints", "body_positions", "velocity", "angular_velocity", "joints_velocity", "body_quaternions")
+
+
+def make_multiclip_data(source, n_frames_per_clip: int | None = None) -> ReferenceClip:
+    """reference `io/load.py:105-137`: stac-mjx arrays `qpos (N, nq)`, `qvel (N, nv)`, `xpos (N, B, 3)`, `xquat (N, B, 4)` with
+    `N = n_clips * n_frames_per_clip` reshaped to `(clips, frames, dims)` and split into the eight ReferenceClip fields.
+
+    `source` is a mapping with those four arrays, or a path to an `.npz` holding them (plus optionally a scalar
+    `n_frames_per_clip`), or a stac-mjx `.h5` file when h5py is importable (it is not in this image; the reference reads the
+    clip length from the file's YAML config in that case)."""
+    if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__"):
+        path = str(source)
+        if path.endswith((".h5", ".hdf5")):
+            try:
+                import h5py  # noqa: PLC0415
+            except ImportError as e:  # pragma: no cover - h5py is absent from this image
+                raise ImportError("reading stac-mjx HDF5 needs h5py; convert to .npz (qpos, qvel, xpos, xquat) instead") from e
+            with h5py.File(path, "r") as f:
+                data = {k: f[k][()] for k in ("qpos", "qvel", "xpos", "xquat")}
+                if n_frames_per_clip is None:
+                    import yaml  # noqa: PLC0415
+
+                    n_frames_per_clip = yaml.safe_load(f["config"][()].decode("utf-8"))["stac"]["n_frames_per_clip"]
+        else:
+            with np.load(path) as f:
+                data = {k: f[k] for k in ("qpos", "qvel", "xpos", "xquat")}
+                if n_frames_per_clip is None and "n_frames_per_clip" in f:
+                    n_frames_per_clip = int(f["n_frames_per_clip"])
+    else:
+        data = {k: np.asarray(source[k]) for k in ("qpos", "qvel", "xpos", "xquat")}
+    if n_frames_per_clip is None:
+        raise ValueError("n_frames_per_clip is required (the reference reads it from the HDF5 config)")
+    L_ = int(n_frames_per_clip)
+    n = data["qpos"].shape[0]
+    if n % L_ or any(data[k].shape[0] != n for k in data):
+        raise ValueError("frame count must be a multiple of n_frames_per_clip and equal across qpos / qvel / xpos / xquat")
+
+    def rs(a):
+        return np.ascontiguousarray(a.reshape(n // L_, L_, *a.shape[1:]), np.float32)
+
+    qpos, qvel, xpos, xquat = rs(data["qpos"]), rs(data["qvel"]), rs(data["xpos"]), rs(data["xquat"])
+    return ReferenceClip(position=qpos[:, :, :3], quaternion=qpos[:, :, 3:7], joints=qpos[:, :, 7:], body_positions=xpos,
+                         velocity=qvel[:, :, :3], angular_velocity=qvel[:, :, 3:6], joints_velocity=qvel[:, :, 6:], body_quaternions=xquat)
+
+
+def to_stac_arrays(clips: ReferenceClip) -> dict[str, np.ndarray]:
+    """Inverse of make_multiclip_data: the flat per-frame arrays stac-mjx stores."""
+    c, f = clips.position.shape[:2]
+    qpos = np.concatenate([clips.position, clips.quaternion, clips.joints], -1).reshape(c * f, -1)
+    qvel = np.concatenate([clips.velocity, clips.angular_velocity, clips.joints_velocity], -1).reshape(c * f, -1)
+    return {"qpos": qpos, "qvel": qvel, "xpos": clips.body_positions.reshape(c * f, *clips.body_positions.shape[2:]),
+            "xquat": clips.body_quaternions.reshape(c * f, *clips.body_quaternions.shape[2:])}
+
+
+def select_clips(clips: ReferenceClip, indices) -> ReferenceClip:
+    """reference `io/load.py:258-278`."""
+    idx = np.asarray(indices)
+    return ReferenceClip(**{k: getattr(clips, k)[idx] for k in _FIELDS}, original_clip_idx=idx[:, None].astype(np.int32))
+
+
+def generate_train_test_split(data: ReferenceClip, test_ratio: float = 0.1, rng: np.random.Generator | None = None):
+    """reference `io/load.py:187-214` (the reference draws from numpy's global RNG; pass `rng` for a reproducible split)."""
+    n = data.position.shape[0]
+    indices = np.arange(n)
+    chooser = rng.choice if rng is not None else np.random.choice
+    test_idx = np.sort(chooser(indices, size=int(n * test_ratio), replace=False))
+    train_idx = indices[~np.isin(indices, test_idx)]
+    return select_clips(data, train_idx), select_clips(data, test_idx)

@@ -1347,7 +1347,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   const int max_iter = m.iterations != 1 ? m.iterations : 1;
   bool active = true;
   for (int iter = 0; iter < max_iter; ++iter) {
-    if (m.sync_level > 0) phase_sync();
+    if (m.sync_mask & 16) phase_sync();
     if (active && m.iterations != 1) {
       const float improvement = (prev_cost - cost) / scale;
       const float gradient = sqrtf(vdot(grad, grad)) / scale;
@@ -1462,11 +1462,11 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   com_pos(w, fo.com);
   if (m.sync_level > 1) phase_sync();
   com_vel_rne(w, fo.bias);
-  if (m.sync_level > 0) phase_sync();
+  if (m.sync_mask & 1) phase_sync();
   passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
   __syncwarp();
   build_m(w);
-  if (m.sync_level > 0) phase_sync();
+  if (m.sync_mask & 2) phase_sync();
   float Maw[kNvSlots];   // M qacc_warmstart, while o_big still holds the raw inertia
   if (m.use_gen) {
     float wv[kNvSlots];
@@ -1480,13 +1480,13 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
   }
   __syncwarp();
   if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1, gen::kNMpad); __syncwarp(); } else factor_dual(w);
-  if (m.sync_level > 0) phase_sync();
+  if (m.sync_mask & 4) phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
   solve_ld(w, w.at(m.o_L), fo.qas);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
-  if (m.sync_level > 0) phase_sync();
+  if (m.sync_mask & 8) phase_sync();
   solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
   vput(w, w.at(m.o_warm), fo.so.qacc);
   __syncwarp();
@@ -2015,6 +2015,8 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
   m->dm.sync_level = 0;  // measured: one barrier per substep keeps the block in lock-step; more only add skew
   if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
+  m->dm.sync_mask = m->dm.sync_level > 0 ? 0x1f : 0;
+  if (const char* e = std::getenv("TMJX_SYNC_MASK")) m->dm.sync_mask = atoi(e);                          // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));

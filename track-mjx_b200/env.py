@@ -101,6 +101,7 @@ class Stepper:
         for name, spec, kind in fields:
             self.buf[name] = torch.zeros((n_env, L.field_size(spec, self.dims)), device=self.device,
                                          dtype=torch.float32 if kind == "f" else torch.int32)
+        self._own_obs = self.buf["obs"]
         self._state_c = L.fill_struct(L.StateC(), L.STATE_FIELDS, self.buf, lambda t: t.data_ptr())
         self._out_c = L.fill_struct(L.OutC(), L.OUT_FIELDS + L.DEBUG_FIELDS, self.buf, lambda t: t.data_ptr())
 
@@ -132,6 +133,16 @@ class Stepper:
             raise ValueError(f"action must have shape ({self.n_env}, {self.dims['nu']})")
         L.check(self.lib, self.lib.tmjx_step(self._model, self._clips, C.c_void_p(action.data_ptr()), C.byref(self._state_c),
                                              C.byref(self._out_c), self.n_env, flags, self._stream()), "tmjx_step")
+
+    def redirect_obs(self, obs: torch.Tensor | None = None):
+        """Point TmjxOut.obs at a caller-owned `[n_env, obs_size]` tensor (e.g. slot t+1 of a rollout buffer) so that the step
+        kernel writes the observation where its consumer wants it; `None` restores the stepper's own buffer."""
+        if obs is None:
+            obs = self._own_obs
+        if obs.shape != self._own_obs.shape or obs.dtype != torch.float32 or not obs.is_contiguous() or obs.device != self.device:
+            raise ValueError("obs target must be a contiguous fp32 [n_env, obs_size] tensor on the env's device")
+        self.buf["obs"] = obs
+        self._out_c.obs = obs.data_ptr()
 
     def clips_device_bytes(self) -> int:
         return int(self.lib.tmjx_clips_device_bytes(self._clips))

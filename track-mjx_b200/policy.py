@@ -108,8 +108,9 @@ class IntentionPolicy:
                     "logits": torch.empty(n, 2 * a, **f), "latent_mean": torch.empty(n, z, **f), "latent_logvar": torch.empty(n, z, **f)}
         self.launches_per_act = int(self.lib.tmjx_policy_launches_per_act(self._p))
 
-    def act(self, obs, eps_latent=None, eps_action=None, deterministic: bool = False):
-        """obs: [n, obs_size] CUDA tensor.  Returns (action, extras) views into buffers owned by the policy."""
+    def act(self, obs, eps_latent=None, eps_action=None, deterministic: bool = False, out=None):
+        """obs: [n, obs_size] CUDA tensor.  Returns (action, extras) views into buffers owned by the policy, or into the
+        caller's `out` tensors (keys of self.out; e.g. slot t of a rollout buffer) when given."""
         t = self.torch
         n = int(obs.shape[0])
         if not deterministic:
@@ -118,7 +119,10 @@ class IntentionPolicy:
             if eps_action is None:
                 eps_action = t.randn(n, self.cfg.action_size, device=self.device)
         ptr = lambda x: None if x is None else C.c_void_p(x.data_ptr())
-        o = self.out
+        o = self.out if out is None else {**self.out, **out}
+        for k, v in o.items():
+            if v.dtype != t.float32 or not v.is_contiguous() or v.shape[0] < n:
+                raise ValueError(f"policy output '{k}' must be a contiguous fp32 tensor with >= {n} rows")
         rc = self.lib.tmjx_policy_act(self._p, ptr(obs), ptr(eps_latent), ptr(eps_action), int(deterministic), ptr(o["action"]),
                                       ptr(o["raw_action"]), ptr(o["log_prob"]), ptr(o["logits"]), ptr(o["latent_mean"]),
                                       ptr(o["latent_logvar"]), n, C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
