@@ -190,6 +190,138 @@ __global__ void __launch_bounds__(THREADS) linear_tf32_kernel(const float* __res
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(BN)) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2: 256 x BN output tile per CTA (two M = 128 accumulators sharing one B tile: the weight tile is fetched half as often
+// and the activation tile N / BN times), warp-specialised: warps 0..6 are cp.async producers that signal a per-stage "full"
+// mbarrier (after cp.async.wait_group + fence.proxy.async on their own writes), one thread of warp 7 waits on it, issues the
+// eight MMAs of the K slice and tcgen05.commit's on the stage's "empty" mbarrier; there is no block barrier in the main loop.
+template <int BN2>
+struct V2 {
+  static constexpr int BM2 = 256, STG = BN2 == 256 ? 3 : 4, NPROD = 224, LAG = 1;
+  static constexpr int kStage = (BM2 + BN2) * BK * 4;
+  static constexpr int kSmem = STG * kStage;
+};
+
+template <int BN2>
+__global__ void __launch_bounds__(THREADS, 1) linear_tf32_v2_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Wt, int ldw,
+                                                                    const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M,
+                                                                    int Kpad, int act) {
+  using C2 = V2<BN2>;
+  constexpr int BM2 = C2::BM2, STG = C2::STG, NPROD = C2::NPROD;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[STG], bar_empty[STG], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+  const int nk = Kpad / BK;
+  const uint32_t sbase = smem_u32(smem);
+  constexpr uint32_t kTmemCols = 2 * BN2;   // 256 or 512: power of two
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  if (tid < NPROD) {
+    // ---- producers
+    auto arrive_full = [&](int kt) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(&bar_full[kt % STG])) : "memory");
+    };
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STG;
+      if (kt >= STG) mbar_wait(&bar_empty[s], uint32_t((kt / STG - 1) & 1));
+      const uint32_t sa = sbase + s * C2::kStage, sb = sa + BM2 * BK * 4;
+      for (int c = tid; c < (BM2 + BN2) * (BK / 4); c += NPROD) {
+        if (c < BM2 * (BK / 4)) {
+          const int r = c >> 3, kc = c & 7;
+          const bool ok = m0 + r < M;
+          cp_async16(sa + (kc * BM2 + r) * 16, X + size_t(ok ? m0 + r : 0) * ldx + kt * BK + kc * 4, ok ? 16u : 0u);
+        } else {
+          const int c2 = c - BM2 * (BK / 4), r = c2 >> 3, kc = c2 & 7;
+          cp_async16(sb + (kc * BN2 + r) * 16, Wt + size_t(n0 + r) * ldw + kt * BK + kc * 4, 16u);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (kt >= 1) {   // LAG = 1: the previous slice has landed
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        arrive_full(kt - 1);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    arrive_full(nk - 1);
+  } else if (tid == NPROD) {
+    // ---- MMA issuer (one thread)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN2 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STG;
+      mbar_wait(&bar_full[s], uint32_t((kt / STG) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = sbase + s * C2::kStage, sb = sa + BM2 * BK * 4;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t db = make_desc(sb + j * 2 * BN2 * 16, uint32_t(BN2 * 16), 128u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t da = make_desc(sa + j * 2 * BM2 * 16 + h * 128 * 16, uint32_t(BM2 * 16), 128u);
+          mma_tf32(tmem + uint32_t(h * BN2), da, db, idesc, (kt > 0 || j > 0) ? 1u : 0u);
+        }
+      }
+      mma_commit(&bar_empty[s]);
+    }
+    mma_commit(&bar_done);
+  }
+  mbar_wait(&bar_done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+
+  // ---- epilogue: warp w -> accumulator half w / 4, TMEM lanes 32 (w % 4) .. +31; thread = one output row, all BN2 columns
+  const int h = warp >> 2, lane_base = (warp & 3) * 32;
+  const int row = m0 + h * 128 + lane_base + lane;
+#pragma unroll 1
+  for (int c = 0; c < BN2; c += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + (uint32_t(lane_base) << 16) + uint32_t(h * BN2 + c);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < M) {
+      float* dst = Y + size_t(row) * ldy + n0 + c;
+      const float* bb = bias + n0 + c;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = __uint_as_float(v[j]) + __ldg(bb + j);
+        o.y = __uint_as_float(v[j + 1]) + __ldg(bb + j + 1);
+        o.z = __uint_as_float(v[j + 2]) + __ldg(bb + j + 2);
+        o.w = __uint_as_float(v[j + 3]) + __ldg(bb + j + 3);
+        if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
 // flax nn.LayerNorm (epsilon 1e-6, use_fast_variance: var = E[x^2] - E[x]^2 clipped at 0), in place; one warp per row
 __global__ void layernorm_kernel(float* __restrict__ Y, int ldy, int n, const float* __restrict__ scale, const float* __restrict__ bias, int M) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -274,7 +406,7 @@ using namespace tmjx_policy;
 
 struct TmjxPolicy {
   TmjxPolicyDesc d;
-  int device = 0, max_env = 0, desc_swap = 0;
+  int device = 0, max_env = 0, desc_swap = 0, use_v1 = 0;
   std::vector<Layer> enc, dec;   // enc: hidden layers + the fused (mean | logvar) head; dec: hidden layers + logits
   float *norm_mean = nullptr, *norm_std = nullptr;
   float* buf[2] = {nullptr, nullptr};   // ping-pong activations [max_env, ld_buf]
@@ -313,6 +445,7 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   auto* p = new TmjxPolicy();
   p->d = *d; p->device = device; p->max_env = max_env;
   if (const char* e = std::getenv("TMJX_POLICY_DESC_SWAP")) p->desc_swap = atoi(e);
+  if (const char* e = std::getenv("TMJX_POLICY_V1")) p->use_v1 = atoi(e);   // A/B knob: the 128 x 128 block-synchronous kernel
   const float* cur = params;
   auto upload = [&](const std::vector<float>& h, float** dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(h.size(), 1) * 4);
@@ -327,7 +460,7 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   }
   // W is flax's Dense kernel [in, out] row-major; the tensor core wants both operands K-major: Wt[out (padded), in (padded)]
   auto dense = [&](int k, int n, const float* W, const float* b, Layer& L) -> cudaError_t {
-    L.k = k; L.n = n; L.kpad = pad_to(k, BK); L.npad = pad_to(n, BN);
+    L.k = k; L.n = n; L.kpad = pad_to(k, BK); L.npad = n > 256 ? pad_to(n, 256) : pad_to(n, BN);
     std::vector<float> wt(size_t(L.npad) * L.kpad, 0.f), bb(L.npad, 0.f);
     for (int i = 0; i < k; ++i) for (int j = 0; j < n; ++j) wt[size_t(j) * L.kpad + i] = W[size_t(i) * n + j];
     for (int j = 0; j < n; ++j) bb[j] = b[j];
@@ -379,6 +512,8 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   PCU(cudaMemset(p->enc_in, 0, size_t(max_env) * p->ld_enc * 4));   // the K padding columns stay zero
   PCU(cudaMemset(p->dec_in, 0, size_t(max_env) * p->ld_dec * 4));
   PCU(cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<128>::kSmem));
   *out = p;
   return TMJX_OK;
 }
@@ -391,8 +526,16 @@ void tmjx_policy_destroy(TmjxPolicy* p) {
 }
 
 static int run_linear(const TmjxPolicy* p, const Layer& L, const float* x, int ldx, float* y, int ldy, int M, cudaStream_t st) {
-  dim3 grid((M + BM - 1) / BM, L.npad / BN);
-  linear_tf32_kernel<<<grid, THREADS, kSmemBytes, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act, p->desc_swap);
+  if (p->use_v1) {
+    dim3 grid((M + BM - 1) / BM, L.npad / BN);
+    linear_tf32_kernel<<<grid, THREADS, kSmemBytes, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act, p->desc_swap);
+  } else if (L.npad >= 512) {   // wide layers: 256 x 256 tiles (one wave of <= 148 CTAs at 16384 rows x 512 columns)
+    dim3 grid((M + 255) / 256, L.npad / 256);
+    linear_tf32_v2_kernel<256><<<grid, THREADS, V2<256>::kSmem, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act);
+  } else {
+    dim3 grid((M + 255) / 256, L.npad / 128);
+    linear_tf32_v2_kernel<128><<<grid, THREADS, V2<128>::kSmem, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act);
+  }
   if (L.ln) layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(y, ldy, L.n, L.ln_scale, L.ln_bias, M);
   PCU(cudaGetLastError());
   return TMJX_OK;
