@@ -16,6 +16,7 @@
  * the tanh-normal action head are small row-wise kernels around the GEMMs.  All launches are enqueued on the caller's
  * stream; nothing is allocated per call.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -194,11 +195,11 @@ __global__ void __launch_bounds__(THREADS) linear_tf32_kernel(const float* __res
 // ---------------------------------------------------------------------------------------------------------------------
 // v2: 256 x BN output tile per CTA (two M = 128 accumulators sharing one B tile: the weight tile is fetched half as often
 // and the activation tile N / BN times), warp-specialised: warps 0..6 are cp.async producers that signal a per-stage "full"
-// mbarrier (after cp.async.wait_group + fence.proxy.async on their own writes), one thread of warp 7 waits on it, issues the
+// mbarrier through cp.async.mbarrier.arrive.noinc (arrival = completion of the thread's copies), one thread of warp 7 waits on it, issues the
 // eight MMAs of the K slice and tcgen05.commit's on the stage's "empty" mbarrier; there is no block barrier in the main loop.
 template <int BN2>
 struct V2 {
-  static constexpr int BM2 = 256, STG = BN2 == 256 ? 3 : 4, NPROD = 224, LAG = 1;
+  static constexpr int BM2 = 256, STG = BN2 == 256 ? 3 : 4, NPROD = 224;
   static constexpr int kStage = (BM2 + BN2) * BK * 4;
   static constexpr int kSmem = STG * kStage;
 };
@@ -233,11 +234,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_v2_kernel(const float*
   const uint32_t tmem = tmem_slot;
 
   if (tid < NPROD) {
-    // ---- producers
-    auto arrive_full = [&](int kt) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(&bar_full[kt % STG])) : "memory");
-    };
+    // ---- producers: never wait on their own loads -- `cp.async.mbarrier.arrive.noinc` makes the completion of this thread's
+    // copies one of the NPROD expected arrivals of the stage's "full" barrier, so up to STG slices are in flight
     for (int kt = 0; kt < nk; ++kt) {
       const int s = kt % STG;
       if (kt >= STG) mbar_wait(&bar_empty[s], uint32_t((kt / STG - 1) & 1));
@@ -252,20 +250,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_v2_kernel(const float*
           cp_async16(sb + (kc * BN2 + r) * 16, Wt + size_t(n0 + r) * ldw + kt * BK + kc * 4, 16u);
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (kt >= 1) {   // LAG = 1: the previous slice has landed
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        arrive_full(kt - 1);
-      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    arrive_full(nk - 1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (tid == NPROD) {
     // ---- MMA issuer (one thread)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN2 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
     for (int kt = 0; kt < nk; ++kt) {
       const int s = kt % STG;
       mbar_wait(&bar_full[s], uint32_t((kt / STG) & 1));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the landed cp.async data (generic proxy) -> tensor-core reads (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sa = sbase + s * C2::kStage, sb = sa + BM2 * BK * 4;
 #pragma unroll
@@ -312,6 +306,135 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_v2_kernel(const float*
         o.y = __uint_as_float(v[j + 1]) + __ldg(bb + j + 1);
         o.z = __uint_as_float(v[j + 2]) + __ldg(bb + j + 2);
         o.w = __uint_as_float(v[j + 3]) + __ldg(bb + j + 3);
+        if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v3 (default): the same 256 x BN tile and accumulator layout as v2, operands moved by TMA.  ncu on v2 showed the producer
+// warps stalled on the scoreboard of their own LDGSTS address registers (one K slice in flight per thread, 15 GB/s per SM);
+// with `cp.async.bulk.tensor.2d` ONE thread issues two bulk copies per K slice (A: 32 floats x 256 rows, B: 32 x BN) that
+// land 128-byte-swizzled (CU_TENSOR_MAP_SWIZZLE_128B) and complete on the stage's "full" mbarrier (expect_tx); the MMA
+// thread reads them through SWIZZLE_128B K-major descriptors (8-row groups 1024 B apart, K advance = +32 B inside the
+// 128-byte atom).  Warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, all 8 warps = epilogue.
+template <int BN2>
+struct V3 {
+  static constexpr int BM2 = 256, STG = BN2 == 256 ? 3 : 4;
+  static constexpr int kABytes = BM2 * BK * 4, kBBytes = BN2 * BK * 4, kStage = kABytes + kBBytes;
+  static constexpr int kSmem = STG * kStage + 1024;   // + slack for the 1024-byte alignment the swizzle needs
+};
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int BN2>
+__global__ void __launch_bounds__(THREADS, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+                                                                     const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
+                                                                     int act) {
+  using C3 = V3<BN2>;
+  constexpr int BM2 = C3::BM2, STG = C3::STG;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[STG], bar_empty[STG], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+  const int nk = Kpad / BK;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kTmemCols = 2 * BN2;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 64) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  if (tid == 0) {
+    // ---- TMA producer
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STG;
+      if (kt >= STG) mbar_wait(&bar_empty[s], uint32_t((kt / STG - 1) & 1));
+      const uint32_t sa = sbase + s * C3::kStage, sb = sa + C3::kABytes;
+      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(&bar_full[s])),
+                   "r"(uint32_t(C3::kStage))
+                   : "memory");
+      tma_load_2d(sa, &mapX, kt * BK, m0, &bar_full[s]);
+      tma_load_2d(sb, &mapW, kt * BK, n0, &bar_full[s]);
+    }
+  } else if (tid == 32) {
+    // ---- MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN2 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STG;
+      mbar_wait(&bar_full[s], uint32_t((kt / STG) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = sbase + s * C3::kStage, sb = sa + C3::kABytes;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t db = make_desc_sw128(sb + j * 32);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t da = make_desc_sw128(sa + h * 128 * 128 + j * 32);
+          mma_tf32(tmem + uint32_t(h * BN2), da, db, idesc, (kt > 0 || j > 0) ? 1u : 0u);
+        }
+      }
+      mma_commit(&bar_empty[s]);
+    }
+    mma_commit(&bar_done);
+  }
+  mbar_wait(&bar_done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+
+  const int h = warp >> 2, lane_base = (warp & 3) * 32;
+  const int row = m0 + h * 128 + lane_base + lane;
+#pragma unroll 1
+  for (int c = 0; c < BN2; c += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + (uint32_t(lane_base) << 16) + uint32_t(h * BN2 + c);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < M) {
+      float* dst = Y + size_t(row) * ldy + n0 + c;
+      const float4* bb = reinterpret_cast<const float4*>(bias + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(bb + (j >> 2));
+        float4 o;
+        o.x = __uint_as_float(v[j]) + b4.x;
+        o.y = __uint_as_float(v[j + 1]) + b4.y;
+        o.z = __uint_as_float(v[j + 2]) + b4.z;
+        o.w = __uint_as_float(v[j + 3]) + b4.w;
         if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
         *reinterpret_cast<float4*>(dst + j) = o;
       }
@@ -398,7 +521,35 @@ __global__ void action_head_kernel(const float* __restrict__ lg, int ld_lg, int 
 struct Layer {
   int k = 0, n = 0, kpad = 0, npad = 0, act = 0, ln = 0;
   float *wt = nullptr, *bias = nullptr, *ln_scale = nullptr, *ln_bias = nullptr;
+  CUtensorMap mapW;                 // [npad rows, kpad] fp32, box 32 x BN, 128-byte swizzle
+  CUtensorMap mapX;                 // the layer's input buffer inside tmjx_policy_act ([max_env rows, kpad], box 32 x 256)
+  const float* x_bound = nullptr;   // the buffer mapX was encoded for
+  int ldx_bound = 0;
 };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// rows x cols fp32 matrix with row pitch ld (floats); box = 32 floats (one 128-byte swizzle atom) x box_rows
+static bool encode_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {32u, cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 }  // namespace tmjx_policy
 
@@ -406,7 +557,7 @@ using namespace tmjx_policy;
 
 struct TmjxPolicy {
   TmjxPolicyDesc d;
-  int device = 0, max_env = 0, desc_swap = 0, use_v1 = 0;
+  int device = 0, max_env = 0, desc_swap = 0, use_v1 = 0;   // use_v1: 0 = TMA kernel, 1 = 128 x 128 block-synchronous, 2 = cp.async warp-specialised
   std::vector<Layer> enc, dec;   // enc: hidden layers + the fused (mean | logvar) head; dec: hidden layers + logits
   float *norm_mean = nullptr, *norm_std = nullptr;
   float* buf[2] = {nullptr, nullptr};   // ping-pong activations [max_env, ld_buf]
@@ -512,6 +663,23 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   PCU(cudaMemset(p->enc_in, 0, size_t(max_env) * p->ld_enc * 4));   // the K padding columns stay zero
   PCU(cudaMemset(p->dec_in, 0, size_t(max_env) * p->ld_dec * 4));
   PCU(cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<128>::kSmem));
+  if (!p->use_v1) {
+    // weight tensor maps once; activation maps for the fixed buffer chain of tmjx_policy_act
+    const float* x = p->enc_in;
+    int ldx = p->ld_enc, pp = 0;
+    auto bind = [&](Layer& L) -> bool {
+      if (!encode_map(&L.mapW, L.wt, L.npad, L.kpad, L.kpad, L.npad >= 512 ? 256 : 128)) return false;
+      if (!encode_map(&L.mapX, x, max_env, L.kpad, ldx, 256)) return false;
+      L.x_bound = x; L.ldx_bound = ldx;
+      x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
+      return true;
+    };
+    for (Layer& L : p->enc) if (!bind(L)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    x = p->dec_in; ldx = p->ld_dec;
+    for (Layer& L : p->dec) if (!bind(L)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+  }
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<256>::kSmem));
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<128>::kSmem));
   *out = p;
@@ -526,7 +694,19 @@ void tmjx_policy_destroy(TmjxPolicy* p) {
 }
 
 static int run_linear(const TmjxPolicy* p, const Layer& L, const float* x, int ldx, float* y, int ldy, int M, cudaStream_t st) {
-  if (p->use_v1) {
+  if (!p->use_v1) {
+    CUtensorMap mx = L.mapX;
+    if (x != L.x_bound || ldx != L.ldx_bound) {   // a caller-owned input (tmjx_policy_linear): encode its map on the fly
+      if (!encode_map(&mx, x, M, L.kpad, ldx, 256)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+    if (L.npad >= 512) {
+      dim3 grid((M + 255) / 256, L.npad / 256);
+      linear_tf32_tma_kernel<256><<<grid, THREADS, V3<256>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act);
+    } else {
+      dim3 grid((M + 255) / 256, L.npad / 128);
+      linear_tf32_tma_kernel<128><<<grid, THREADS, V3<128>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act);
+    }
+  } else if (p->use_v1 == 1) {
     dim3 grid((M + BM - 1) / BM, L.npad / BN);
     linear_tf32_kernel<<<grid, THREADS, kSmemBytes, st>>>(x, ldx, L.wt, L.kpad, L.bias, y, ldy, M, L.kpad, L.act, p->desc_swap);
   } else if (L.npad >= 512) {   // wide layers: 256 x 256 tiles (one wave of <= 148 CTAs at 16384 rows x 512 columns)
