@@ -72,6 +72,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }   // MUFU.EX2 + MUFU.RCP, ~2 ulp
+constexpr int kTmaThreads = 512;
 
 // Y[M, ldy] (columns n0 .. n0 + 127 of this block) = act(X[M, K] * Wt[N, K]^T + bias).  X / Wt row pitches ldx / ldw are
 // multiples of BK floats and zero padded; Wt and bias are padded to a multiple of BN rows.
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_v2_kernel(const float*
 // with `cp.async.bulk.tensor.2d` ONE thread issues two bulk copies per K slice (A: 32 floats x 256 rows, B: 32 x BN) that
 // land 128-byte-swizzled (CU_TENSOR_MAP_SWIZZLE_128B) and complete on the stage's "full" mbarrier (expect_tx); the MMA
 // thread reads them through SWIZZLE_128B K-major descriptors (8-row groups 1024 B apart, K advance = +32 B inside the
-// 128-byte atom).  Warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, all 8 warps = epilogue.
+// 128-byte atom).  Warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, all 16 warps = epilogue.
 template <int BN2>
 struct V3 {
   static constexpr int BM2 = 256, STG = BN2 == 256 ? 3 : 4;
@@ -339,7 +341,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 
 template <int BN2>
-__global__ void __launch_bounds__(THREADS, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+__global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
                                                                      const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
                                                                      int act) {
   using C3 = V3<BN2>;
@@ -408,10 +410,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_tma_kernel(const __gri
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
 
-  const int h = warp >> 2, lane_base = (warp & 3) * 32;
+  // ---- epilogue, 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 of accumulator (w / 4) % 2, column half w / 8;
+  // thread = one output row.  (Four warps per scheduler: with two, the bias / SiLU chain was latency-bound and the epilogue
+  // took as long as the main loop; a shared-memory transpose for 128-byte stores measured slower than the direct form.)
+  const int h = (warp >> 2) & 1, lane_base = (warp & 3) * 32, chalf = warp >> 3;
   const int row = m0 + h * 128 + lane_base + lane;
+  const int c_beg = chalf * (BN2 / 2), c_end = (act & 4) ? c_beg : c_beg + BN2 / 2;   // bit 2: timing experiment only (skip the epilogue)
+  act &= 1;
 #pragma unroll 1
-  for (int c = 0; c < BN2; c += 32) {
+  for (int c = c_beg; c < c_end; c += 32) {
     uint32_t v[32];
     const uint32_t taddr = tmem + (uint32_t(lane_base) << 16) + uint32_t(h * BN2 + c);
     asm volatile(
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32_tma_kernel(const __gri
         o.y = __uint_as_float(v[j + 1]) + b4.y;
         o.z = __uint_as_float(v[j + 2]) + b4.z;
         o.w = __uint_as_float(v[j + 3]) + b4.w;
-        if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        if (act) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
         *reinterpret_cast<float4*>(dst + j) = o;
       }
     }
@@ -558,6 +565,7 @@ using namespace tmjx_policy;
 struct TmjxPolicy {
   TmjxPolicyDesc d;
   int device = 0, max_env = 0, desc_swap = 0, use_v1 = 0;   // use_v1: 0 = TMA kernel, 1 = 128 x 128 block-synchronous, 2 = cp.async warp-specialised
+  int skip_epi = 0;   // timing experiment knob (TMJX_POLICY_SKIP_EPI=1): results are invalid
   std::vector<Layer> enc, dec;   // enc: hidden layers + the fused (mean | logvar) head; dec: hidden layers + logits
   float *norm_mean = nullptr, *norm_std = nullptr;
   float* buf[2] = {nullptr, nullptr};   // ping-pong activations [max_env, ld_buf]
@@ -596,7 +604,8 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   auto* p = new TmjxPolicy();
   p->d = *d; p->device = device; p->max_env = max_env;
   if (const char* e = std::getenv("TMJX_POLICY_DESC_SWAP")) p->desc_swap = atoi(e);
-  if (const char* e = std::getenv("TMJX_POLICY_V1")) p->use_v1 = atoi(e);   // A/B knob: the 128 x 128 block-synchronous kernel
+  if (const char* e = std::getenv("TMJX_POLICY_V1")) p->use_v1 = atoi(e);
+  if (const char* e = std::getenv("TMJX_POLICY_SKIP_EPI")) p->skip_epi = atoi(e) ? 4 : 0;   // A/B knob: the 128 x 128 block-synchronous kernel
   const float* cur = params;
   auto upload = [&](const std::vector<float>& h, float** dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(h.size(), 1) * 4);
@@ -701,10 +710,10 @@ static int run_linear(const TmjxPolicy* p, const Layer& L, const float* x, int l
     }
     if (L.npad >= 512) {
       dim3 grid((M + 255) / 256, L.npad / 256);
-      linear_tf32_tma_kernel<256><<<grid, THREADS, V3<256>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act);
+      linear_tf32_tma_kernel<256><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act | p->skip_epi);
     } else {
       dim3 grid((M + 255) / 256, L.npad / 128);
-      linear_tf32_tma_kernel<128><<<grid, THREADS, V3<128>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act);
+      linear_tf32_tma_kernel<128><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mx, L.mapW, L.bias, y, ldy, M, L.kpad, L.act | p->skip_epi);
     }
   } else if (p->use_v1 == 1) {
     dim3 grid((M + BM - 1) / BM, L.npad / BN);
