@@ -251,7 +251,11 @@ __device__ __forceinline__ void scan_ancestors(const Warp& w, float* buf) {
       const int a = b < m.nbody ? int(m.anc_pow[r * m.nbody + b]) : 0;
       on[s] = a != 0;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) add[s][k] = on[s] ? buf[a * NC + k] : 0.f;
+      for (int k = 0; k < NC; k += 2) {   // float2: half the LDS, no 2-way bank conflict of the stride-NC scalar form
+        float2 t2 = make_float2(0.f, 0.f);
+        if (on[s]) t2 = *reinterpret_cast<const float2*>(buf + a * NC + k);
+        add[s][k] = t2.x; add[s][k + 1] = t2.y;
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -259,7 +263,10 @@ __device__ __forceinline__ void scan_ancestors(const Warp& w, float* buf) {
       if (!on[s]) continue;
       const int b = w.lane + 32 * s;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) { acc[s][k] += add[s][k]; buf[b * NC + k] = acc[s][k]; }
+      for (int k = 0; k < NC; k += 2) {
+        acc[s][k] += add[s][k]; acc[s][k + 1] += add[s][k + 1];
+        *reinterpret_cast<float2*>(buf + b * NC + k) = make_float2(acc[s][k], acc[s][k + 1]);
+      }
     }
     __syncwarp();
   }
@@ -291,15 +298,15 @@ __device__ __forceinline__ void sum_subtrees(const Warp& w, float* buf) {
       const int cnt = int(p >> 16);
       on[s] = cnt != 0;
       if (cnt == 1) {
-        const float* src = buf + int(p & 0xffffu) * NC;
+        const float2* src = reinterpret_cast<const float2*>(buf + int(p & 0xffffu) * NC);
 #pragma unroll
-        for (int k = 0; k < NC; ++k) acc[s][k] += src[k];
+        for (int k = 0; k < NC / 2; ++k) { const float2 t2 = src[k]; acc[s][2 * k] += t2.x; acc[s][2 * k + 1] += t2.y; }
       } else if (cnt > 1) {
         const int e0 = int(p & 0xffffu);
         for (int e = e0; e < e0 + cnt; ++e) {
-          const float* src = buf + int(m.dsc_list[e]) * NC;
+          const float2* src = reinterpret_cast<const float2*>(buf + int(m.dsc_list[e]) * NC);
 #pragma unroll
-          for (int k = 0; k < NC; ++k) acc[s][k] += src[k];
+          for (int k = 0; k < NC / 2; ++k) { const float2 t2 = src[k]; acc[s][2 * k] += t2.x; acc[s][2 * k + 1] += t2.y; }
         }
       }
     }
@@ -309,7 +316,7 @@ __device__ __forceinline__ void sum_subtrees(const Warp& w, float* buf) {
       if (!on[s]) continue;
       const int b = w.lane + 32 * s;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) buf[b * NC + k] = acc[s][k];
+      for (int k = 0; k < NC; k += 2) *reinterpret_cast<float2*>(buf + b * NC + k) = make_float2(acc[s][k], acc[s][k + 1]);
     }
     __syncwarp();
   }
@@ -372,7 +379,7 @@ __device__ void kinematics(const Warp& w) {
     for (int k = 0; k < 4; ++k) Q[s][k] = quat[k];
     if (b < m.nbody) {
       xpos[b * 3] = pos[0]; xpos[b * 3 + 1] = pos[1]; xpos[b * 3 + 2] = pos[2];
-      xquat[b * 4] = quat[0]; xquat[b * 4 + 1] = quat[1]; xquat[b * 4 + 2] = quat[2]; xquat[b * 4 + 3] = quat[3];
+      *reinterpret_cast<float4*>(xquat + b * 4) = make_float4(quat[0], quat[1], quat[2], quat[3]);
     }
   }
   __syncwarp();
@@ -387,8 +394,7 @@ __device__ void kinematics(const Warp& w) {
       if (on[s]) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) Pa[s][k] = xpos[a * 3 + k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) Qa[s][k] = xquat[a * 4 + k];
+        { const float4 q4 = *reinterpret_cast<const float4*>(xquat + a * 4); Qa[s][0] = q4.x; Qa[s][1] = q4.y; Qa[s][2] = q4.z; Qa[s][3] = q4.w; }
       }
     }
     __syncwarp();
@@ -402,7 +408,8 @@ __device__ void kinematics(const Warp& w) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { P[s][k] = Pa[s][k] + t[k]; xpos[b * 3 + k] = P[s][k]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { Q[s][k] = q2[k]; xquat[b * 4 + k] = q2[k]; }
+      for (int k = 0; k < 4; ++k) Q[s][k] = q2[k];
+      *reinterpret_cast<float4*>(xquat + b * 4) = make_float4(q2[0], q2[1], q2[2], q2[3]);
     }
     __syncwarp();
   }
