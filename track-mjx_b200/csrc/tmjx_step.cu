@@ -458,7 +458,7 @@ __device__ void com_pos(const Warp& w, float com[3]) {
     const float I0 = m.body_inertia[b * 3], I1 = m.body_inertia[b * 3 + 1], I2 = m.body_inertia[b * 3 + 2], ms = m.body_mass[b];
     const float off[3] = {xipos[b * 3] - com[0], xipos[b * 3 + 1] - com[1], xipos[b * 3 + 2] - com[2]};
     const float oo = dot3(off, off);
-    float* ci = cin + b * 10;
+    float ci[10];
 #define INRC(r, c) (R[r * 3] * I0 * R[c * 3] + R[r * 3 + 1] * I1 * R[c * 3 + 1] + R[r * 3 + 2] * I2 * R[c * 3 + 2])
     ci[0] = INRC(0, 0) + (oo - off[0] * off[0]) * ms;
     ci[1] = INRC(1, 1) + (oo - off[1] * off[1]) * ms;
@@ -468,10 +468,11 @@ __device__ void com_pos(const Warp& w, float com[3]) {
     ci[5] = INRC(1, 2) + (0.f - off[1] * off[2]) * ms;
 #undef INRC
     ci[6] = off[0] * ms; ci[7] = off[1] * ms; ci[8] = off[2] * ms; ci[9] = ms;
+    st_rec<10>(cin + b * 10, ci);
   }
   for (int d = w.lane; d < m.nv; d += 32) {
     const int j = m.dof_jnt[d];
-    float* cd = cdof + d * 6;
+    float cd[6];
     const float off[3] = {com[0] - anchor[j * 3], com[1] - anchor[j * 3 + 1], com[2] - anchor[j * 3 + 2]};
     if (m.jnt_type[j] == kJntFree) {
       const int r = d - m.jnt_dofadr[j];
@@ -491,6 +492,7 @@ __device__ void com_pos(const Warp& w, float com[3]) {
       cd[0] = a[0]; cd[1] = a[1]; cd[2] = a[2];
       cross3(a, off, cd + 3);
     }
+    st_rec<6>(cdof + d * 6, cd);
   }
   (void)qpos;
   __syncwarp();
@@ -907,7 +909,8 @@ __device__ void apply_J(const Warp& w, const Rows& r, const float* x, float jv[k
   __syncwarp();
   jv[0] = jv[1] = jv[2] = jv[3] = 0.f;
   if (w.lane < m.ncon && r.cact) {
-    const float* V = sV + m.con_cb[w.lane] * 6;
+    float V[6];
+    ld_rec<6>(sV + m.con_cb[w.lane] * 6, V);
     const float* off = w.at(m.o_cin + m.c_off) + w.lane * 3;
     const float* t1 = w.at(m.o_cin + m.c_t1) + w.lane * 3;
     float vel[3], t2[3];
@@ -942,8 +945,8 @@ __device__ void apply_JT(const Warp& w, const Rows& r, const float f[kRowSlots],
     fw[1] = m.plane_n[1] * fn + t1[1] * f1 + t2[1] * f2;
     fw[2] = m.plane_n[2] * fn + t1[2] * f1 + t2[2] * f2;
     cross3(off, fw, tau);
-    float* o = sW + w.lane * 6;
-    o[0] = tau[0]; o[1] = tau[1]; o[2] = tau[2]; o[3] = fw[0]; o[4] = fw[1]; o[5] = fw[2];
+    const float o6[6] = {tau[0], tau[1], tau[2], fw[0], fw[1], fw[2]};
+    st_rec<6>(sW + w.lane * 6, o6);
   }
 #pragma unroll
   for (int q = 0; q < kLimSlots; ++q) {
