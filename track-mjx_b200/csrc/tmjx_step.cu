@@ -276,7 +276,66 @@ __device__ __forceinline__ void scan_ancestors(const Warp& w, float* buf) {
 // The per-(round, body) descriptors are fetched up front (independent loads) so that the rounds only touch shared memory.
 constexpr int kMaxRounds = 6;  // trees up to 64 levels deep
 template <int NC>
+__device__ __forceinline__ void sum_subtrees_list(const Warp& w, float* buf);
+
+// Default form: the round loop is NOT unrolled (the code of one round stays in the instruction cache for the other five;
+// the unrolled form spent a third of its samples waiting for instruction fetch), the descriptor of the next round is
+// fetched while the current one runs, and a body's (<= 4) descendants at distance 2^r come packed in one word: the
+// gather is a warp-uniform loop of dsc_maxc[r][slot] predicated float2 accumulations instead of a divergent list walk.
+template <int NC>
 __device__ __forceinline__ void sum_subtrees(const Warp& w, float* buf) {
+  const DevModel& m = w.m;
+  if (!m.use_dsc4) { sum_subtrees_list<NC>(w, buf); return; }
+  float acc[kBodySlots][NC];
+  uint32_t pk[kBodySlots];
+#pragma unroll
+  for (int s = 0; s < kBodySlots; ++s) {
+    const int b = w.lane + 32 * s;
+    pk[s] = (b < m.nbody && m.nround > 0) ? m.dsc4[b] : 0u;
+    if (b < m.nbody) ld_rec<NC>(buf + b * NC, acc[s]);
+    else {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) acc[s][k] = 0.f;
+    }
+  }
+#pragma unroll 1
+  for (int r = 0; r < m.nround; ++r) {
+    uint32_t nx[kBodySlots];
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      const int b = w.lane + 32 * s;
+      nx[s] = (b < m.nbody && r + 1 < m.nround) ? m.dsc4[(r + 1) * m.nbody + b] : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      const int maxc = m.dsc_maxc[r][s];
+      uint32_t p = pk[s];
+      for (int i = 0; i < maxc; ++i, p >>= 8) {
+        const int id = int(p & 0xffu);
+        if (id) {
+          const float2* src = reinterpret_cast<const float2*>(buf + id * NC);
+#pragma unroll
+          for (int k = 0; k < NC / 2; ++k) { const float2 t2 = src[k]; acc[s][2 * k] += t2.x; acc[s][2 * k + 1] += t2.y; }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) {
+      if (!pk[s]) continue;
+      const int b = w.lane + 32 * s;
+#pragma unroll
+      for (int k = 0; k < NC; k += 2) *reinterpret_cast<float2*>(buf + b * NC + k) = make_float2(acc[s][k], acc[s][k + 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kBodySlots; ++s) pk[s] = nx[s];
+  }
+}
+
+// list form (any number of descendants per distance): the fallback for trees the packed form cannot describe
+template <int NC>
+__device__ __forceinline__ void sum_subtrees_list(const Warp& w, float* buf) {
   const DevModel& m = w.m;
   float acc[kBodySlots][NC];
   uint32_t pack[kBodySlots][kMaxRounds];

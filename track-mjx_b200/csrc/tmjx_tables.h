@@ -54,6 +54,11 @@ struct DevModel {
   /* dsc_pack[r * nbody + b] = count << 16 | (count == 1 ? the descendant : first index into dsc_list): one load per
    * (round, body) on the common path (chains: at most one descendant at each distance) */
   const uint32_t* dsc_pack;
+  /* dsc4[r * nbody + b] = up to four descendant ids at distance 2^r, one per byte (0 = none); dsc_maxc[r][slot] = the largest
+   * count among the bodies lane + 32 slot (warp-uniform trip count of the gather); use_dsc4 = every count <= 4 */
+  const uint32_t* dsc4;
+  uint8_t dsc_maxc[8][4];
+  int use_dsc4;
   /* per sparse-inertia entry e = lane + 32 it: row | col << 8, two iterations per word:
    * m_rc2[lane + 32 h] = rc[lane + 32 (2 h)] | rc[lane + 32 (2 h + 1)] << 16 */
   const uint32_t* m_rc2;
@@ -229,6 +234,18 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     for (int i = 0; i < nbody; ++i) {
       const int e0 = dsc_start[size_t(r) * (nbody + 1) + i], e1 = dsc_start[size_t(r) * (nbody + 1) + i + 1], cnt = e1 - e0;
       dsc_pack[size_t(r) * nbody + i] = int32_t((uint32_t(cnt) << 16) | uint32_t(cnt == 1 ? dsc_list[e0] : e0));
+    }
+  std::vector<int32_t> dsc4(size_t(std::max(nround, 1)) * nbody, 0);
+  m.use_dsc4 = (nround <= 8 && nbody <= 96) ? 1 : 0;
+  std::memset(m.dsc_maxc, 0, sizeof(m.dsc_maxc));
+  for (int r = 0; r < nround && m.use_dsc4; ++r)
+    for (int i = 0; i < nbody; ++i) {
+      const int e0 = dsc_start[size_t(r) * (nbody + 1) + i], e1 = dsc_start[size_t(r) * (nbody + 1) + i + 1], cnt = e1 - e0;
+      if (cnt > 4) { m.use_dsc4 = 0; break; }
+      uint32_t pk = 0;
+      for (int e = 0; e < cnt; ++e) pk |= uint32_t(dsc_list[e0 + e]) << (8 * e);
+      dsc4[size_t(r) * nbody + i] = int32_t(pk);
+      m.dsc_maxc[r][i / 32] = uint8_t(std::max<int>(m.dsc_maxc[r][i / 32], cnt));
     }
   if (dsc_start.empty()) dsc_start.push_back(0);
   if (dsc_list.empty()) dsc_list.push_back(0);
@@ -505,6 +522,7 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   PF(dof_armature, b.f32("dof_armature")); PF(dof_damping, b.f32("dof_damping"));
   P8(anc_pow, anc_pow); P8(dsc_list, dsc_list);
   m.dsc_pack = TMJX_OFF(uint32_t, push(t.i32, dsc_pack));
+  m.dsc4 = TMJX_OFF(uint32_t, push(t.i32, dsc4));
   {
     if (m.nM > 1280) throw std::runtime_error("more than 1280 inertia entries unsupported");
     std::vector<int32_t> rc2(32 * 20, 0);
@@ -586,6 +604,7 @@ inline void relocate(DevModel& m, const int* di, const uint16_t* d16, const uint
   RF(dof_armature); RF(dof_damping);
   R8(anc_pow); R8(dsc_list);
   m.dsc_pack = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dsc_pack);
+  m.dsc4 = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dsc4);
   m.seg_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.seg_task);
   m.cb_task = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.cb_task);
   m.dof_seg3 = reinterpret_cast<const uint32_t*>(di) + reinterpret_cast<uintptr_t>(m.dof_seg3);
