@@ -1523,9 +1523,9 @@ struct FwdOut {
   SolverOut so;
 };
 
-__device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist) {
+__device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_here = true) {
   const DevModel& m = w.m;
-  if (m.sync_level >= 0) phase_sync();
+  if (m.sync_level >= 0 && sync_here) phase_sync();
   kinematics(w);
   if (m.sync_level > 1) phase_sync();
   com_pos(w, fo.com);
@@ -1738,7 +1738,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
     float* dbg_dist = (live && a.out.dbg_contact_dist) ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
     if (kStep) {
       for (int f = 0; f < m.n_frames; ++f) {
-        forward(w, fo, f == m.n_frames - 1 ? dbg_dist : nullptr);
+        forward(w, fo, f == m.n_frames - 1 ? dbg_dist : nullptr, m.sync_every <= 1 || f % m.sync_every == 0);
         euler(w, fo, time);
       }
     } else {
@@ -2086,6 +2086,8 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
   m->dm.sync_mask = m->dm.sync_level > 0 ? 0x1f : 0;
   if (const char* e = std::getenv("TMJX_SYNC_MASK")) m->dm.sync_mask = atoi(e);                          // tuning knob
+  m->dm.sync_every = 1;
+  if (const char* e = std::getenv("TMJX_SYNC_EVERY")) m->dm.sync_every = std::max(1, atoi(e));           // tuning knob
   m->smem_per_block = per_env * m->envs_per_block;
   if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
   m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
