@@ -268,3 +268,31 @@ def test_c_abi_error_paths(walker, clips2):
     o = L.OutC()
     assert lib.tmjx_step(g._model, g._clips, None, C.byref(s), C.byref(o), 8, 0, None) == -1
     g.close()
+
+
+@pytest.mark.parametrize("knob", ["TMJX_NO_SEG", "TMJX_NO_DSC4", "TMJX_NO_GEN", "TMJX_ENVS_PER_BLOCK"])
+def test_generic_fallback_paths_match_the_specialised_ones(walker, clips2, knob, monkeypatch):
+    """The tree-generic code paths (contact-chain loops instead of segments, list walk instead of packed descendants, table
+    loops instead of the generated factorisation / solves, 4-warp blocks) stay selectable for other walkers; they must give
+    the specialised paths' results on the rodent: one physics substep agrees to fp32 reassociation noise."""
+    n = 48
+    st = rollout_states(walker, clips2, n, 6, 0.1, seed=5)
+    cfg = make_cfg(walker, physics_steps_per_control_step=1)
+    act = np.random.default_rng(2).normal(size=(n, walker.nu)).astype(np.float32)
+
+    def run():
+        g = Stepper(walker.blob, cfg, clips2, n, 0, debug=True)
+        common.put(g.buf, st)
+        g.step(torch.from_numpy(act).cuda())
+        torch.cuda.synchronize()
+        out = common.get(g.buf, ("qpos", "qvel", "obs", "reward", "done", "cur_frame"))
+        g.close()
+        return out
+
+    ref = run()
+    monkeypatch.setenv(knob, "4" if knob == "TMJX_ENVS_PER_BLOCK" else "1")
+    alt = run()
+    assert np.array_equal(ref["done"], alt["done"]) and np.array_equal(ref["cur_frame"], alt["cur_frame"])
+    for k in ("qpos", "qvel", "obs", "reward"):
+        abs_err, rel = common.err(alt[k], ref[k])
+        assert rel < 2e-4, (knob, k, abs_err, rel)

@@ -2082,6 +2082,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
+  if (const char* e = std::getenv("TMJX_NO_DSC4")) { if (atoi(e)) m->dm.use_dsc4 = 0; }                  // tuning knob
   m->dm.sync_level = 0;  // measured: one barrier per substep keeps the block in lock-step; more only add skew
   if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
   m->dm.sync_mask = m->dm.sync_level > 0 ? 0x1f : 0;
