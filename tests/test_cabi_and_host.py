@@ -143,3 +143,23 @@ def test_multiclip_loader_round_trip(walker, tmp_path):
     both = np.sort(np.concatenate([train.original_clip_idx[:, 0], test.original_clip_idx[:, 0]]))
     assert np.array_equal(both, np.arange(5))
     assert np.array_equal(test.joints, again.joints[test.original_clip_idx[:, 0]])
+
+
+def test_bench_reference_arm_prints_one_schema_complete_json_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints exactly one JSON line on stdout
+    with the keys the measurement contract names."""
+    import json
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+              "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -9,12 +9,15 @@
  *
  * B200 mapping: every Dense layer is one tcgen05 GEMM over the environment batch -- `tcgen05.mma.cta_group::1.kind::tf32`
  * (fp32 operands read as TF32 by the tensor core, fp32 accumulation in TMEM; XLA's default fp32 matmul precision on
- * NVIDIA GPUs is TF32 as well), 128 x 128 output tiles, one elected thread issues the MMAs, operands are staged in shared
- * memory by a 3-deep cp.async ring in the canonical no-swizzle K-major core-matrix layout, stage reuse is tracked by
- * `tcgen05.commit` on mbarriers, the epilogue reads the accumulator with `tcgen05.ld` (thread = output row), adds the
- * bias, applies SiLU and writes fp32 activations.  LayerNorm, observation normalisation, the reparameterised latent and
- * the tanh-normal action head are small row-wise kernels around the GEMMs.  All launches are enqueued on the caller's
- * stream; nothing is allocated per call.
+ * NVIDIA GPUs is TF32 as well).  Three kernels live here, newest first:
+ *   linear_tf32_tma_kernel<BN>  (default)  256 x BN tile = two M = 128 accumulators sharing one B tile, operands moved by TMA
+ *                                (cp.async.bulk.tensor.2d, 128-byte swizzle, expect_tx mbarriers), one producer thread, one MMA
+ *                                thread, 16-warp tcgen05.ld epilogue (bias, SiLU);
+ *   linear_tf32_v2_kernel<BN>   (TMJX_POLICY_V1=2)  the same tile with warp-specialised cp.async producers;
+ *   linear_tf32_kernel          (TMJX_POLICY_V1=1)  128 x 128 tile, block-synchronous cp.async ring.
+ * The older two are kept as A/B references (DESIGN.md 3b has the measurements that led from one to the next).  LayerNorm,
+ * observation normalisation, the reparameterised latent and the tanh-normal action head are small row-wise kernels around
+ * the GEMMs.  All launches are enqueued on the caller's stream; nothing is allocated per call.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
