@@ -1397,7 +1397,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     for (int q = 0; q < kNvSlots; ++q) Mgrad[q] = grad[q];
     if (newton) {  // H = M + J^T diag(D active) J, assembled and factored in the o_L block (same tree sparsity as M)
       build_hessian(w, r, Jaref);
-      if (m.use_gen) { __syncwarp(); gen::factor_dual(w.at(m.o_L), w.lane, false, 0); __syncwarp(); }
+      if (m.use_gen) { __syncwarp(); gen::factor_dual(w.at(m.o_L), w.lane, false, 0); __syncwarp(); }   // inside `if (active)`: no block barrier here
       else factor_single(w, w.at(m.o_L));
     }
     solve_ld(w, L1, Mgrad);
@@ -1493,7 +1493,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
       for (int k = 0; k < kRowSlots; ++k) Jaref[k] += jv[k] * alpha;
     }
     }
-    if (m.sync_level > 1) phase_sync();
+    if (m.sync_mask & 64) phase_sync();
     if (active) {
     // ---- body: update + Polak-Ribiere
     float pg[kNvSlots], pMg[kNvSlots];
@@ -2085,7 +2085,9 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_NO_DSC4")) { if (atoi(e)) m->dm.use_dsc4 = 0; }                  // tuning knob
   m->dm.sync_level = 0;  // measured: one barrier per substep keeps the block in lock-step; more only add skew
   if (const char* e = std::getenv("TMJX_SYNC")) m->dm.sync_level = atoi(e);                              // tuning knob
-  m->dm.sync_mask = m->dm.sync_level > 0 ? 0x1f : 0;
+  // Newton: one barrier per solver iteration (the iteration re-runs the 70 KB generated factorisation; without it the
+  // 10 warps drift apart inside a substep: ncu showed 28 % instruction-fetch + 28 % barrier stalls, +18 % with the barrier)
+  m->dm.sync_mask = m->dm.sync_level > 0 ? 0x1f : (is_newton ? 16 : 0);
   if (const char* e = std::getenv("TMJX_SYNC_MASK")) m->dm.sync_mask = atoi(e);                          // tuning knob
   m->dm.sync_every = 1;
   if (const char* e = std::getenv("TMJX_SYNC_EVERY")) m->dm.sync_every = std::max(1, atoi(e));           // tuning knob

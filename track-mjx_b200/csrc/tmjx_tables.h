@@ -84,7 +84,7 @@ struct DevModel {
   uint16_t u_ancre[1280];
   int use_gen;                /* the dof tree equals the one csrc/tmjx_gen_tree.cuh was generated for */
   int sync_every;             /* the substep barrier is taken every sync_every-th substep (1 = every substep) */
-  int sync_mask;              /* extra phase barriers: 1 after com_vel_rne, 2 after build_m, 4 after the factorisation, 8 before the solver, 16 per solver iteration */
+  int sync_mask;              /* extra phase barriers: 1 after com_vel_rne, 2 after build_m, 4 after the factorisation, 8 before the solver, 16 per solver iteration (default for Newton), 64 after the line search */
   int sync_level;             /* 2: every phase barrier, 1: major phases only, 0: once per substep (block-uniform) */
   /* factorisation pair table: for step k the entries [pair_start[k], pair_start[k+1]) = a | b << 8 | target << 16 */
   const uint32_t* pair_tab;
