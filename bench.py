@@ -317,6 +317,21 @@ def run_ours(args, rank, world, local_rank):
                 "peak_source": hbm_src},
     }
 
+    # counters of the same kernel from the committed ncu capture (static evidence, not measured in this run)
+    try:
+        import glob
+
+        cap = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_kernel_ncu_full.json")))[-1]
+        cj = json.load(open(cap))
+        pick = {"issue_slots_busy_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "fma_pipe_active_pct": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                "lsu_wavefronts_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                "registers_per_thread": "launch__registers_per_thread", "warp_instructions": "smsp__inst_executed.sum"}
+        roofline["ncu_counters"] = {k: float(cj[v][0]) for k, v in pick.items() if v in cj}
+        roofline["ncu_counters"]["source"] = os.path.relpath(cap, ROOT)
+    except (IndexError, OSError, ValueError, KeyError):
+        pass
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline and args.workload == "tracking":
         cpu_baseline = cpu_baseline_leg(walker, clips, config)
