@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -586,6 +587,8 @@ extern "C" {
 
 const char* tmjx_policy_last_error(void) { return g_perr.c_str(); }
 
+void tmjx_policy_destroy(TmjxPolicy* p);
+
 size_t tmjx_policy_param_count(const TmjxPolicyDesc* d) {
   if (!d) return 0;
   size_t n = 2 * size_t(d->obs_size);
@@ -605,6 +608,7 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   if (n_params != tmjx_policy_param_count(d)) return pfail(TMJX_E_ARG, "parameter vector has the wrong length");
   PCU(cudaSetDevice(device));
   auto* p = new TmjxPolicy();
+  std::unique_ptr<TmjxPolicy, void (*)(TmjxPolicy*)> guard(p, tmjx_policy_destroy);   // error returns below free what was built
   p->d = *d; p->device = device; p->max_env = max_env;
   if (const char* e = std::getenv("TMJX_POLICY_DESC_SWAP")) p->desc_swap = atoi(e);
   if (const char* e = std::getenv("TMJX_POLICY_V1")) p->use_v1 = atoi(e);
@@ -694,7 +698,7 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   }
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<256>::kSmem));
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<128>::kSmem));
-  *out = p;
+  *out = guard.release();
   return TMJX_OK;
 }
 

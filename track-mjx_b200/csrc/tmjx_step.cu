@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -2041,6 +2042,8 @@ extern "C" {
 int tmjx_abi_version(void) { return TMJX_ABI_VERSION; }
 const char* tmjx_last_error(void) { return g_err.c_str(); }
 
+void tmjx_model_destroy(TmjxModel* m);
+
 int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg, int device, TmjxModel** out) {
   if (!blob || !cfg || !out) return fail(TMJX_E_ARG, "null argument");
   if (cfg->abi_version != TMJX_ABI_VERSION) return fail(TMJX_E_ARG, "TmjxTaskConfig.abi_version mismatch");
@@ -2054,6 +2057,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   }
   CU(cudaSetDevice(device));
   auto* m = new TmjxModel();
+  std::unique_ptr<TmjxModel, void (*)(TmjxModel*)> guard(m, tmjx_model_destroy);   // error returns below free what was built
   m->device = device;
   m->cfg = *cfg;
   CU(cudaMalloc(&m->d_i32, std::max<size_t>(t.i32.size(), 1) * 4));
@@ -2096,7 +2100,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
   const int dyn = int(m->smem_per_block);
   CU(m->envs_per_block == 14 ? variant_attr_14(dyn) : (m->envs_per_block == 10 ? variant_attr_10(dyn) : variant_attr_4(dyn)));
-  *out = m;
+  *out = guard.release();
   return TMJX_OK;
 }
 
@@ -2116,6 +2120,8 @@ int tmjx_model_dims(const TmjxModel* m, TmjxDims* d) {
   d->smem_bytes_per_env = m->dm.smem_floats * 4; d->envs_per_block = m->envs_per_block; d->threads_per_env = 32;
   return TMJX_OK;
 }
+
+void tmjx_clips_destroy(TmjxClips* c);
 
 int tmjx_clips_create(const TmjxModel* m, const float* position, const float* quaternion, const float* joints,
                       const float* body_positions, const float* velocity, const float* angular_velocity,
@@ -2141,10 +2147,11 @@ int tmjx_clips_create(const TmjxModel* m, const float* position, const float* qu
   }
   CU(cudaSetDevice(m->device));
   auto* c = new TmjxClips();
+  std::unique_ptr<TmjxClips, void (*)(TmjxClips*)> cguard(c, tmjx_clips_destroy);
   c->device = m->device; c->n_clips = n_clips; c->clip_len = clip_len; c->bytes = tab.size() * 4;
   CU(cudaMalloc(&c->d_table, c->bytes));
   CU(cudaMemcpy(c->d_table, tab.data(), c->bytes, cudaMemcpyHostToDevice));
-  *out = c;
+  *out = cguard.release();
   return TMJX_OK;
 }
 void tmjx_clips_destroy(TmjxClips* c) {
