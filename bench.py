@@ -265,7 +265,8 @@ def run_ours(args, rank, world, local_rank):
             d_ea.copy_(h_ea[i % 4], non_blocking=True)
             a = policy.act(st.obs, d_ez, d_ea)[0]
         st = env.step(st, a)
-        h_obs.copy_(st.obs, non_blocking=True)
+        if policy is None:   # with the policy in the loop the observation is consumed on the device; the host reads the metrics
+            h_obs.copy_(st.obs, non_blocking=True)
         h_rew.copy_(st.reward, non_blocking=True)
         h_done.copy_(st.done, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller needs the host results before the next action
@@ -281,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     e2e_value = ENVS_PER_GPU * world * K / max_over_ranks(e2e_s, dev, shard)
     h2d = ENVS_PER_GPU * (env.action_size if policy is None else pcfg.latent_size + pcfg.action_size) * 4
-    d2h = ENVS_PER_GPU * (obs_dim + 2) * 4
+    d2h = ENVS_PER_GPU * ((obs_dim if policy is None else 0) + 2) * 4
 
     if rank != 0:
         if dist is not None:
