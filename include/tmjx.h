@@ -223,6 +223,13 @@ int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_late
 int tmjx_policy_linear(const TmjxPolicy* p, int which, const float* x, int ldx, float* y, int ldy, int n_env, void* stream);
 int tmjx_policy_launches_per_act(const TmjxPolicy* p);
 
+/* Generalised Advantage Estimation over a rollout (first piece of the learner side).  Replaces
+ *   compute_gae   reference track_mjx/agent/mlp_ppo/losses.py:39-101
+ * All arrays are DEVICE pointers, time-major [T, B] fp32 (bootstrap_value [B]); outputs vs and advantages [T, B].  Same
+ * float32 operation order as the reference, no fused multiply-add: bit-identical to its numpy execution. */
+int tmjx_gae(const float* truncation, const float* termination, const float* rewards, const float* values, const float* bootstrap_value,
+             float lambda, float discount, float* vs, float* advantages, int T, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -529,6 +529,32 @@ __global__ void action_head_kernel(const float* __restrict__ lg, int ld_lg, int 
   if (logits) for (int i = lane; i < 2 * na; i += 32) logits[size_t(row) * 2 * na + i] = l[i];
 }
 
+
+// Generalised Advantage Estimation (reference losses.py:39-101 `compute_gae`): one thread per environment walks its T steps
+// backwards; [T, B] arrays are read / written with consecutive threads on consecutive environments (coalesced), every
+// element exactly once: 24 B per (t, env), HBM-bound.  The arithmetic follows the reference's float32 operation order with
+// explicit round-to-nearest multiplies and adds (no fused multiply-add), so the result is bit-identical to the restatement.
+__global__ void gae_kernel(const float* __restrict__ truncation, const float* __restrict__ termination, const float* __restrict__ rewards,
+                           const float* __restrict__ values, const float* __restrict__ bootstrap, float lambda, float discount,
+                           float* __restrict__ vs, float* __restrict__ advantages, int T, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float acc = 0.f, v_next = bootstrap[b], vs_next = bootstrap[b];
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = size_t(t) * B + b;
+    const float tm = __fsub_rn(1.f, truncation[i]);
+    const float dn = __fmul_rn(discount, __fsub_rn(1.f, termination[i]));   // discount * (1 - termination)
+    const float r = rewards[i], v = values[i];
+    const float delta = __fmul_rn(__fsub_rn(__fadd_rn(r, __fmul_rn(dn, v_next)), v), tm);
+    acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(dn, tm), lambda), acc));
+    const float vs_t = __fadd_rn(acc, v);
+    advantages[i] = __fmul_rn(__fsub_rn(__fadd_rn(r, __fmul_rn(dn, vs_next)), v), tm);
+    vs[i] = vs_t;
+    v_next = v;
+    vs_next = vs_t;
+  }
+}
+
 struct Layer {
   int k = 0, n = 0, kpad = 0, npad = 0, act = 0, ln = 0;
   float *wt = nullptr, *bias = nullptr, *ln_scale = nullptr, *ln_bias = nullptr;
@@ -775,6 +801,16 @@ int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_late
     x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
   }
   action_head_kernel<<<(n_env + 7) / 8, 256, 0, st>>>(x, ldx, d.action_size, eps_action, deterministic, action, raw_action, log_prob, logits, n_env);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+int tmjx_gae(const float* truncation, const float* termination, const float* rewards, const float* values, const float* bootstrap_value,
+             float lambda, float discount, float* vs, float* advantages, int T, int B, void* stream) {
+  if (!truncation || !termination || !rewards || !values || !bootstrap_value || !vs || !advantages) return pfail(TMJX_E_ARG, "null argument");
+  if (T <= 0 || B <= 0) return pfail(TMJX_E_ARG, "T and B must be positive");
+  gae_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(truncation, termination, rewards, values, bootstrap_value, lambda,
+                                                                           discount, vs, advantages, T, B);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }
