@@ -230,6 +230,26 @@ int tmjx_policy_launches_per_act(const TmjxPolicy* p);
 int tmjx_gae(const float* truncation, const float* termination, const float* rewards, const float* values, const float* bootstrap_value,
              float lambda, float discount, float* vs, float* advantages, int T, int B, void* stream);
 
+/* Observation-normaliser statistics (the state `running_statistics.normalize` reads).  Replaces
+ *   running_statistics.update   reference track_mjx/agent/masked_running_statistics.py:80-214 (as called at ppo.py:357-361)
+ * in three steps so that a multi-GPU caller can all-reduce between them (the reference psums twice inside `update`); the batch
+ * is read ONCE (step 1), steps 2 and 3 touch [D] vectors only:
+ *   1 tmjx_running_stats_sums : over the LOCAL batch [N, D]: sums[0..D) = sum_rows (x - mean), sums[D..2D) = batch mean,
+ *                               sums[2D..3D) = sum_rows (x - batch mean)^2                  -> all-reduce sums[0..D) and N
+ *   2 tmjx_running_stats_mean : u = sums[0..D) / (count + increment); mean += u (in place);
+ *                               sums[0..D) = this GPU's share of sum_rows (x - old mean)(x - new mean)   -> all-reduce sums[0..D)
+ *   3 tmjx_running_stats_apply: count += increment; summed_variance += var;
+ *                               std = clip(sqrt(max(summed_variance, 0) / count), std_min, std_max)       (in place)
+ * All pointers are DEVICE pointers (count, increment: one float each); sums: 3 D floats; scratch >=
+ * tmjx_running_stats_scratch_floats(D) floats, the same buffer for the three calls of one update. */
+size_t tmjx_running_stats_scratch_floats(int D);
+int tmjx_running_stats_sums(const float* batch, int N, int D, const float* mean, float* sums, float* scratch, void* stream);
+int tmjx_running_stats_mean(float* sums, const float* increment, int n_local, int D, const float* count, float* mean, float* scratch,
+                            void* stream);
+int tmjx_running_stats_apply(const float* var, int D, float std_min, float std_max, float* count, float* summed_variance, float* std,
+                             const float* scratch, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,53 @@
+"""Device timings of the learner-side kernels (GAE, observation-normaliser update) at BASELINE configs[2] sizes.
+
+    python tools/gpu_learner_bench.py > gpurun_out/learner_bench.json
+
+Normaliser: one training step's observations (unroll 20 x 16384 envs x 696 floats = 912 MB, larger than L2); algorithmic
+traffic = one read of the batch.  GAE: [20, 16384] x 4 inputs + 2 outputs.  CUDA events on the current stream, 3 warm-ups.
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from track_mjx_b200.learner import RunningStatistics, compute_gae  # noqa: E402
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    T, B, D = 20, 16384, 696
+    peaks = {}
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peaks = json.load(open(p))
+    x = torch.randn(T * B, D, device="cuda") * 2 + 1
+    st = RunningStatistics(D)
+    ms = timed(lambda: st.update(x))
+    gb = x.numel() * 4 / 1e9
+    out = {"running_stats": {"rows": T * B, "D": D, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3)}}
+    tr = torch.zeros(T, B, device="cuda")
+    te = (torch.rand(T, B, device="cuda") < 0.02).float()
+    r, v, bv = torch.rand(T, B, device="cuda"), torch.randn(T, B, device="cuda"), torch.randn(B, device="cuda")
+    ms = timed(lambda: compute_gae(tr, te, r, v, bv, 0.95, 0.95), reps=50)
+    gb = (6 * T * B + B) * 4 / 1e9
+    out["gae"] = {"T": T, "B": B, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3)}
+    out["peaks"] = peaks
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

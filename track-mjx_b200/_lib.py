@@ -121,6 +121,11 @@ def load() -> C.CDLL:
     lib.tmjx_policy_act.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.tmjx_policy_linear.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp]
     lib.tmjx_policy_launches_per_act.argtypes = [vp]
+    lib.tmjx_running_stats_scratch_floats.argtypes = [i32]
+    lib.tmjx_running_stats_scratch_floats.restype = sz
+    lib.tmjx_running_stats_sums.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.tmjx_running_stats_mean.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.tmjx_running_stats_apply.argtypes = [vp, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp]
     lib.tmjx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, vp]
     if lib.tmjx_abi_version() != 1:
         raise ImportError("libtmjx.so ABI version mismatch")

@@ -555,6 +555,140 @@ __global__ void gae_kernel(const float* __restrict__ truncation, const float* __
   }
 }
 
+// Observation-normaliser update (reference masked_running_statistics.py:80-214, called at ppo.py:357-361).  HBM-bound: ONE
+// pass over the [N, D] batch (the reference reads it twice), consecutive threads on consecutive columns (coalesced rows), each
+// block owns a contiguous slab of rows and keeps, per column, sum(x - p) and sum((x - p)^2) about a pivot p = the slab's first
+// row (a sample of the distribution, so the two-sum variance has no catastrophic cancellation even when the running mean is
+// far from the data, as it is on the first update).  Slab moments (mean, M2) are merged in a fixed block order with the
+// pairwise-update formula (deterministic, no atomics).  The reference's sum((x - m)(x - m')) with m' = m + u equals
+// M2 + n (xbar - m)(xbar - m'), which the two small kernels after the all-reduce of sum(x - m) evaluate (stats_mean_kernel).
+constexpr int kStatThreads = 256, kStatColsPerThread = 4;   // D <= 1024
+constexpr int kStatBlocks = 148 * 4;                          // row slabs: four resident blocks per SM
+__global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float* __restrict__ x, int N, int D, float* __restrict__ partial) {
+  const int rows_per_block = (N + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  if (r0 >= r1) return;
+  float p[kStatColsPerThread], s1[kStatColsPerThread], s2[kStatColsPerThread];
+#pragma unroll
+  for (int j = 0; j < kStatColsPerThread; ++j) {
+    const int c = threadIdx.x + kStatThreads * j;
+    p[j] = c < D ? x[size_t(r0) * D + c] : 0.f; s1[j] = 0.f; s2[j] = 0.f;
+  }
+  for (int r = r0 + 1; r < r1; ++r) {
+    const float* row = x + size_t(r) * D;
+#pragma unroll
+    for (int j = 0; j < kStatColsPerThread; ++j) {
+      const int c = threadIdx.x + kStatThreads * j;
+      if (c < D) { const float d = row[c] - p[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
+    }
+  }
+  const float n = float(r1 - r0);
+#pragma unroll
+  for (int j = 0; j < kStatColsPerThread; ++j) {
+    const int c = threadIdx.x + kStatThreads * j;
+    if (c < D) {
+      const float dm = s1[j] / n;
+      partial[(size_t(blockIdx.x) * 2) * D + c] = p[j] + dm;                              // slab mean
+      partial[(size_t(blockIdx.x) * 2 + 1) * D + c] = fmaxf(s2[j] - dm * s1[j], 0.f);     // slab M2 = sum (x - slab mean)^2
+    }
+  }
+}
+// The same slab moments with 16-byte loads (D % 4 == 0, which the tracking observations satisfy: 696 = 4 x 174).  Block =
+// 32 float4 columns (one 512-byte row segment per warp-row) x 8 row lanes, four independent loads in flight per thread; all
+// lanes share the slab's first row as the pivot, so their sums simply add (fixed lane order, deterministic).  Grid = column
+// chunks x kStatSlabs row slabs (6 x 192 = 1152 blocks for D = 696: ~8 resident blocks per SM).
+constexpr int kStatTx = 32, kStatTy = 8, kStatSlabs = 192;
+__device__ __forceinline__ void stat_acc(const float4 v, const float4 p, float4& s1, float4& s2) {
+  const float dx = v.x - p.x, dy = v.y - p.y, dz = v.z - p.z, dw = v.w - p.w;
+  s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+  s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+}
+__global__ void __launch_bounds__(kStatTx* kStatTy) stats_partial_vec_kernel(const float4* __restrict__ x, int N, int D4, float* __restrict__ partial) {
+  __shared__ float4 sh1[kStatTy][kStatTx], sh2[kStatTy][kStatTx];
+  const int c4 = blockIdx.x * kStatTx + threadIdx.x;
+  const int rows_per_slab = (N + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(N, r0 + rows_per_slab);
+  if (r0 >= r1) return;
+  const bool live = c4 < D4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p = zero, s1 = zero, s2 = zero;
+  if (live) {
+    const float4* col = x + c4;
+    p = __ldg(col + size_t(r0) * D4);
+    int r = r0 + 1 + threadIdx.y;
+    for (; r + 3 * kStatTy < r1; r += 4 * kStatTy) {
+      const float4 v0 = __ldcs(col + size_t(r) * D4), v1 = __ldcs(col + size_t(r + kStatTy) * D4),
+                   v2 = __ldcs(col + size_t(r + 2 * kStatTy) * D4), v3 = __ldcs(col + size_t(r + 3 * kStatTy) * D4);
+      stat_acc(v0, p, s1, s2); stat_acc(v1, p, s1, s2); stat_acc(v2, p, s1, s2); stat_acc(v3, p, s1, s2);
+    }
+    for (; r < r1; r += kStatTy) stat_acc(__ldcs(col + size_t(r) * D4), p, s1, s2);
+  }
+  sh1[threadIdx.y][threadIdx.x] = s1; sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    for (int l = 1; l < kStatTy; ++l) {
+      const float4 a = sh1[l][threadIdx.x], b = sh2[l][threadIdx.x];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    const float n = float(r1 - r0);
+    const float4 dm = make_float4(s1.x / n, s1.y / n, s1.z / n, s1.w / n);
+    float4* out = reinterpret_cast<float4*>(partial + (size_t(blockIdx.y) * 2) * (4 * size_t(D4))) + c4;
+    out[0] = make_float4(p.x + dm.x, p.y + dm.y, p.z + dm.z, p.w + dm.w);
+    out[D4] = make_float4(fmaxf(s2.x - dm.x * s1.x, 0.f), fmaxf(s2.y - dm.y * s1.y, 0.f), fmaxf(s2.z - dm.z * s1.z, 0.f),
+                          fmaxf(s2.w - dm.w * s1.w, 0.f));
+  }
+}
+// Fixed-order merge of the slab moments; out[0..D) = sum(x - mean) = N (xbar - mean), out[D..2D) = xbar, out[2D..3D) = M2
+__global__ void stats_combine_kernel(const float* __restrict__ partial, int N, int nblk, int D, const float* __restrict__ mean,
+                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const int rows_per_block = (N + nblk - 1) / nblk;
+  float n = 0.f, mu = 0.f, m2 = 0.f;
+  for (int b = 0; b < nblk; ++b) {
+    const int r0 = b * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    if (r0 >= r1) break;
+    const float nb = float(r1 - r0), mb = partial[(size_t(b) * 2) * D + c], qb = partial[(size_t(b) * 2 + 1) * D + c];
+    const float nt = n + nb, delta = mb - mu;
+    mu += delta * (nb / nt);
+    m2 += qb + delta * delta * (n * nb / nt);
+    n = nt;
+  }
+  out[c] = n * (mu - mean[c]);
+  out[D + c] = mu;
+  out[2 * D + c] = m2;
+}
+// After sum(x - mean) [D] and the row count were summed over the GPUs: new count (to a side cell), mean update in place and this
+// GPU's share of the variance update, left where sum(x - mean) was.  With d = xbar_local - m, g = S1 / N_total (global batch
+// mean - m) and u = S1 / count' the reference's sum_local (x - m)(x - m - u) summed over the GPUs equals the sum of
+//   M2_local + n_local ((d - g)^2 + g^2 count_old / count')
+// -- every term non-negative: no cancellation against the rounding of the stored mean, which costs the reference's own float32
+// evaluation up to 1e-4 of the variance on the first update
+__global__ void stats_mean_kernel(float* __restrict__ sums, const float* __restrict__ increment, int n_local, int D, const float* __restrict__ count,
+                                  float* __restrict__ mean, float* __restrict__ count_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const float cnt0 = count[0], inc = increment[0], cnt = cnt0 + inc;
+  if (c < D) {
+    const float s1 = sums[c], m = mean[c], d = sums[D + c] - m, g = s1 / inc, e = d - g;
+    mean[c] = m + s1 / cnt;
+    sums[c] = sums[2 * D + c] + float(n_local) * (e * e + g * g * (cnt0 / cnt));
+  }
+  if (c == 0) count_out[0] = cnt;   // a second cell, so that every thread reads the old count
+}
+// After the variance shares were summed over the GPUs: summed_variance += var; std = clip(sqrt(max(sv, 0) / count)); count commit
+__global__ void stats_apply_kernel(const float* __restrict__ var, int D, float std_min, float std_max, const float* __restrict__ count_new,
+                                   float* __restrict__ count, float* __restrict__ sv, float* __restrict__ stdv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const float cnt = count_new[0];
+  if (c < D) {
+    const float v = sv[c] + var[c];
+    sv[c] = v;
+    stdv[c] = fminf(fmaxf(sqrtf(fmaxf(v, 0.f) / cnt), std_min), std_max);
+  }
+  if (c == 0) count[0] = cnt;
+}
+
 struct Layer {
   int k = 0, n = 0, kpad = 0, npad = 0, act = 0, ln = 0;
   float *wt = nullptr, *bias = nullptr, *ln_scale = nullptr, *ln_bias = nullptr;
@@ -811,6 +945,41 @@ int tmjx_gae(const float* truncation, const float* termination, const float* rew
   if (T <= 0 || B <= 0) return pfail(TMJX_E_ARG, "T and B must be positive");
   gae_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(truncation, termination, rewards, values, bootstrap_value, lambda,
                                                                            discount, vs, advantages, T, B);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+/* Observation normaliser, see include/tmjx.h.  scratch: at least tmjx_running_stats_scratch_floats(D) floats. */
+size_t tmjx_running_stats_scratch_floats(int D) { return size_t(kStatBlocks) * 2 * size_t(D) + 1; }
+int tmjx_running_stats_sums(const float* batch, int N, int D, const float* mean, float* sums, float* scratch, void* stream) {
+  if (!batch || !mean || !sums || !scratch) return pfail(TMJX_E_ARG, "null argument");
+  if (N <= 0 || D <= 0 || D > kStatThreads * kStatColsPerThread) return pfail(TMJX_E_ARG, "bad batch shape (D <= 1024)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nblk = std::min(kStatBlocks, N);
+  if (D % 4 == 0 && reinterpret_cast<uintptr_t>(batch) % 16 == 0 && reinterpret_cast<uintptr_t>(scratch) % 16 == 0) {
+    nblk = std::min(kStatSlabs, N);
+    stats_partial_vec_kernel<<<dim3((D / 4 + kStatTx - 1) / kStatTx, nblk), dim3(kStatTx, kStatTy), 0, st>>>(
+        reinterpret_cast<const float4*>(batch), N, D / 4, scratch);
+  } else {
+    stats_partial_kernel<<<nblk, kStatThreads, 0, st>>>(batch, N, D, scratch);
+  }
+  stats_combine_kernel<<<(D + 255) / 256, 256, 0, st>>>(scratch, N, nblk, D, mean, sums);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+int tmjx_running_stats_mean(float* sums, const float* increment, int n_local, int D, const float* count, float* mean, float* scratch,
+                            void* stream) {
+  if (!sums || !increment || !count || !mean || !scratch) return pfail(TMJX_E_ARG, "null argument");
+  if (n_local < 0 || D <= 0) return pfail(TMJX_E_ARG, "bad shape");
+  stats_mean_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, increment, n_local, D, count, mean, scratch);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+int tmjx_running_stats_apply(const float* var, int D, float std_min, float std_max, float* count, float* summed_variance, float* std,
+                             const float* scratch, void* stream) {
+  if (!var || !count || !summed_variance || !std || !scratch) return pfail(TMJX_E_ARG, "null argument");
+  if (D <= 0) return pfail(TMJX_E_ARG, "bad shape");
+  stats_apply_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(var, D, std_min, std_max, scratch, count, summed_variance, std);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }

@@ -30,3 +30,52 @@ def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambd
     if rc != 0:
         raise RuntimeError(f"tmjx_gae failed ({rc}): {lib.tmjx_policy_last_error().decode()}")
     return vs, adv
+
+
+class RunningStatistics:
+    """`RunningStatisticsState` + `update` of `track_mjx/agent/masked_running_statistics.py:34-214` on the GPU (no mask / weights,
+    the way `ppo.py:357-361` calls it).  `update(batch)` accepts any leading batch dimensions; with an initialised
+    `torch.distributed` process group the column sums and the row count are all-reduced (NCCL) between the two kernels, which is
+    what `pmap_axis_name` does in the reference.  `mean` / `std` are what `IntentionPolicy` takes as `norm/mean`, `norm/std`."""
+
+    def __init__(self, size: int, device: int = 0, std_min_value: float = 1e-6, std_max_value: float = 1e6):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("RunningStatistics needs a CUDA device: there is no CPU fallback")
+        self.torch, self.lib, self.D = torch, L.load(), int(size)
+        dev = torch.device("cuda", device)
+        f = dict(dtype=torch.float32, device=dev)
+        self.count = torch.zeros(1, **f)
+        self.mean = torch.zeros(size, **f)
+        self.summed_variance = torch.zeros(size, **f)
+        self.std = torch.ones(size, **f)
+        self._buf = torch.zeros(3 * size + 1, **f)           # row count | sum(x - mean) | batch mean | batch M2
+        self._scratch = torch.zeros(int(self.lib.tmjx_running_stats_scratch_floats(size)), **f)
+        self.std_min, self.std_max = float(std_min_value), float(std_max_value)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+
+    def update(self, batch, all_reduce: bool | None = None):
+        t, lib, D = self.torch, self.lib, self.D
+        x = batch.reshape(-1, D).to(t.float32).contiguous()
+        n = int(x.shape[0])
+        st = C.c_void_p(t.cuda.current_stream(x.device).cuda_stream)
+        ptr = lambda a, off=0: C.c_void_p(a.data_ptr() + 4 * off)
+        dist = t.distributed
+        if all_reduce is None:
+            all_reduce = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        sums, inc = ptr(self._buf, 1), ptr(self._buf, 0)
+        self._check(lib.tmjx_running_stats_sums(ptr(x), n, D, ptr(self.mean), sums, ptr(self._scratch), st), "tmjx_running_stats_sums")
+        self._buf[0] = float(n)
+        if all_reduce:
+            dist.all_reduce(self._buf[: D + 1])               # SUM over ranks: row count and sum(x - mean)   (psum at :163-166)
+        self._check(lib.tmjx_running_stats_mean(sums, inc, n, D, ptr(self.count), ptr(self.mean), ptr(self._scratch), st),
+                    "tmjx_running_stats_mean")
+        if all_reduce:
+            dist.all_reduce(self._buf[1 : D + 1])             # SUM over ranks: variance update                (psum at :176-177)
+        self._check(lib.tmjx_running_stats_apply(sums, D, self.std_min, self.std_max, ptr(self.count), ptr(self.summed_variance),
+                                                 ptr(self.std), ptr(self._scratch), st), "tmjx_running_stats_apply")
+        return self
