@@ -249,6 +249,26 @@ int tmjx_running_stats_mean(float* sums, const float* increment, int n_local, in
 int tmjx_running_stats_apply(const float* var, int D, float std_min, float std_max, float* count, float* summed_variance, float* std,
                              const float* scratch, void* stream);
 
+/* PPO loss head: everything of `compute_ppo_loss` after the network applications.  Replaces
+ *   compute_ppo_loss   reference track_mjx/agent/mlp_ppo/losses.py:154-245 (+ compute_gae :39-101 inside it)
+ * and additionally returns the gradients a backward pass through the networks starts from.  All arrays are DEVICE pointers,
+ * time-major fp32: logits [T, B, 2A] (loc | raw scale of brax's NormalTanhDistribution), latent_mean / latent_logvar [T, B, L],
+ * baseline / reward / discount / truncation / behaviour_log_prob [T, B], bootstrap_value [B], raw_action [T, B, A], eps_entropy
+ * [T, B, A] (the standard-normal draw the reference takes from `entropy_key`).  Outputs: losses[8] = total, policy, value,
+ * latent KL, entropy loss, advantage mean, advantage std, 1 / (std + 1e-8); vs [T, B]; advantages [T, B] (normalised when
+ * hyper->normalize_advantage); d_logits [T, B, 2A], d_latent_mean / d_latent_logvar [T, B, L], d_baseline [T, B] = d total /
+ * d input (vs and advantages are stop_gradient in the reference, so the bootstrap value has no gradient).  scratch >=
+ * tmjx_ppo_loss_scratch_floats(T, B) floats.  Deterministic (fixed summation order). */
+typedef struct TmjxPpoHyper {
+  float entropy_cost, kl_weight, discounting, reward_scaling, gae_lambda, clipping_epsilon;
+  int32_t normalize_advantage;
+} TmjxPpoHyper;
+size_t tmjx_ppo_loss_scratch_floats(int T, int B);
+int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const float* latent_logvar, const float* baseline,
+                       const float* bootstrap_value, const float* reward, const float* discount, const float* truncation,
+                       const float* raw_action, const float* behaviour_log_prob, const float* eps_entropy, int T, int B, int A, int L,
+                       const TmjxPpoHyper* hyper, float* losses, float* vs, float* advantages, float* d_logits, float* d_latent_mean,
+                       float* d_latent_logvar, float* d_baseline, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,8 @@
 
     python tools/gpu_learner_bench.py > gpurun_out/learner_bench.json
 
-Normaliser: one training step's observations (unroll 20 x 16384 envs x 696 floats = 912 MB, larger than L2); algorithmic
+Loss head: 20 x 16384 transitions, 38 actions, 60 latents (all inputs read and all gradients written once = 1.9 KB per row;
+the timing includes the wrapper's output allocations).  Normaliser: one training step's observations (unroll 20 x 16384 envs x 696 floats = 912 MB, larger than L2); algorithmic
 traffic = one read of the batch.  GAE: [20, 16384] x 4 inputs + 2 outputs.  CUDA events on the current stream, 3 warm-ups.
 """
 import json
@@ -12,7 +13,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from track_mjx_b200.learner import RunningStatistics, compute_gae  # noqa: E402
+from track_mjx_b200.learner import RunningStatistics, compute_gae, ppo_loss_head  # noqa: E402
 
 
 def timed(fn, reps=10):
@@ -45,7 +46,15 @@ def main():
     ms = timed(lambda: compute_gae(tr, te, r, v, bv, 0.95, 0.95), reps=50)
     gb = (6 * T * B + B) * 4 / 1e9
     out["gae"] = {"T": T, "B": B, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3)}
-    out["peaks"] = peaks
+    A, Lz = 38, 60
+    g = lambda *shape: torch.randn(*shape, device="cuda")
+    logits, mu, lv, raw, eps, blp = g(T, B, 2 * A) * 0.5, g(T, B, Lz), g(T, B, Lz) * 0.5 - 1, g(T, B, A), g(T, B, A), g(T, B) * 0.3 - 40
+    disc = 1 - te
+    ms = timed(lambda: ppo_loss_head(logits, mu, lv, v, bv, r, disc, tr, raw, blp, eps), reps=20)
+    # every input once (2A + A + A + 2L + 6 floats per row) + every output once (2A + 2L + 3)
+    gb = T * B * (4 * A + 2 * Lz + 6 + 2 * A + 2 * Lz + 3) * 4 / 1e9
+    out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 5}
+    out["peaks"] = {k: peaks.get(k) for k in ("hbm_gbs", "gpu_name")}
     print(json.dumps(out))
 
 

@@ -126,6 +126,9 @@ def load() -> C.CDLL:
     lib.tmjx_running_stats_sums.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.tmjx_running_stats_mean.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     lib.tmjx_running_stats_apply.argtypes = [vp, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp]
+    lib.tmjx_ppo_loss_scratch_floats.argtypes = [i32, i32]
+    lib.tmjx_ppo_loss_scratch_floats.restype = sz
+    lib.tmjx_ppo_loss_head.argtypes = [vp] * 11 + [i32] * 4 + [vp] * 10
     lib.tmjx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, vp]
     if lib.tmjx_abi_version() != 1:
         raise ImportError("libtmjx.so ABI version mismatch")

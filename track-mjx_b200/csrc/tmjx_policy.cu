@@ -555,6 +555,155 @@ __global__ void gae_kernel(const float* __restrict__ truncation, const float* __
   }
 }
 
+// ---- PPO loss head (reference losses.py:104-245 after the network applications) ---------------------------------------
+// Three passes over the [T, B] rollout, one warp per transition row in the two wide ones (lanes over the 38 actions and the 60
+// latent dimensions, coalesced row reads, xor-shuffle sums: deterministic):
+//   ppo_rows_kernel   target log-prob, entropy and latent-KL row sums                       (reads ~1.3 KB per row, HBM-bound)
+//   ppo_reduce_kernel advantage mean / std, then the five loss terms (one block, fixed summation order, [T B] vectors from L2)
+//   ppo_grad_kernel   d loss / d (logits, latent mean, latent log-variance, baseline) + the normalised advantages
+// The gradients are what a backward pass through the policy / value networks starts from; vs and advantages carry no gradient
+// (stop_gradient at losses.py:100), the bootstrap value therefore gets none.
+struct PpoHyper { float entropy_cost, kl_weight, discounting, reward_scaling, gae_lambda, clipping_epsilon; int normalize_advantage; };
+constexpr float kArAlpha = 0.95f, kArPriorVar = 1.f - 0.95f * 0.95f;   // autoregressive latent prior, losses.py:201-202
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float log_det_tanh(float x) { return 2.f * (0.69314718055994531f - x - softplus(-2.f * x)); }
+
+__global__ void ppo_prep_kernel(const float* __restrict__ reward, const float* __restrict__ discount, const float* __restrict__ truncation,
+                                float reward_scaling, float* __restrict__ rewards, float* __restrict__ termination, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rewards[i] = reward[i] * reward_scaling;                          // losses.py:157
+  termination[i] = (1.f - discount[i]) * (1.f - truncation[i]);     // :159
+}
+
+__global__ void __launch_bounds__(256) ppo_rows_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
+                                                       const float* __restrict__ eps, const float* __restrict__ lat_mean,
+                                                       const float* __restrict__ lat_logvar, int T, int B, int A, int L,
+                                                       float* __restrict__ logp, float* __restrict__ ent, float* __restrict__ kl) {
+  const size_t row = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nrow = size_t(T) * B;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrow) return;
+  const float* lg = logits + row * 2 * A;
+  float lp = 0.f, en = 0.f;
+  for (int i = lane; i < A; i += 32) {
+    const float loc = lg[i], scale = softplus(lg[A + i]) + 0.001f, raw = raw_action[row * A + i];
+    const float z = (raw - loc) / scale, ls = logf(scale);
+    lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh(raw);
+    en += 0.5f + 0.91893853320467274f + ls + log_det_tanh(fmaf(scale, eps[row * A + i], loc));
+  }
+  const bool first = row < size_t(B);                               // t == 0: standard normal prior, else AR(1) prior
+  const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L;
+  float k = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float m = mu[j], v = lv[j];
+    if (first) {
+      k += 1.f + v - m * m - expf(v);                               // * -0.5 below (:206-208)
+    } else {
+      const float dm = kArAlpha * mp[j] - m;
+      k += expf(v) / kArPriorVar + dm * dm / kArPriorVar - 1.f + (logf(kArPriorVar) - v);   // * 0.5 below (:221-226)
+    }
+  }
+  lp = warp_sum(lp); en = warp_sum(en); k = warp_sum(k);
+  if (lane == 0) { logp[row] = lp; ent[row] = en; kl[row] = first ? -0.5f * k : 0.5f * k; }
+}
+
+// block-wide sum in a fixed order (thread-sequential, warp xor tree, warps in index order); result valid in every thread
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < int(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+// out: [0] total [1] policy [2] value [3] latent KL [4] entropy loss [5] advantage mean [6] advantage std [7] 1 / (std + 1e-8)
+__global__ void __launch_bounds__(1024) ppo_reduce_kernel(const float* __restrict__ adv, const float* __restrict__ vs,
+                                                          const float* __restrict__ baseline, const float* __restrict__ logp,
+                                                          const float* __restrict__ behaviour_logp, const float* __restrict__ ent,
+                                                          const float* __restrict__ kl, int T, int B, int L, PpoHyper hp,
+                                                          float* __restrict__ out) {
+  __shared__ float sh[32];
+  const size_t n = size_t(T) * B;
+  float mean = 0.f, stdv = 1.f, inv = 1.f;
+  if (hp.normalize_advantage) {                                     // :175-176 (population standard deviation)
+    float s = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += adv[i];
+    mean = block_sum(s, sh) / float(n);
+    s = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) { const float d = adv[i] - mean; s = fmaf(d, d, s); }
+    stdv = sqrtf(block_sum(s, sh) / float(n));
+    inv = 1.f / (stdv + 1e-8f);
+  }
+  float sp = 0.f, sv = 0.f, se = 0.f, k0 = 0.f, kt = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = (adv[i] - mean) * inv, rho = expf(logp[i] - behaviour_logp[i]);                  // :177
+    sp += fminf(rho * a, fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon) * a);   // :179-184
+    const float e = vs[i] - baseline[i];
+    sv = fmaf(e, e, sv);                                            // :187-188
+    se += ent[i];
+    if (i < size_t(B)) k0 += kl[i]; else kt += kl[i];
+  }
+  sp = block_sum(sp, sh); sv = block_sum(sv, sh); se = block_sum(se, sh); k0 = block_sum(k0, sh); kt = block_sum(kt, sh);
+  if (threadIdx.x == 0) {
+    const float policy = -sp / float(n), value = sv / float(n) * 0.5f * 0.5f, entropy = hp.entropy_cost * -(se / float(n));
+    const float kl0 = k0 / (float(B) * L);
+    float klat = hp.kl_weight * kl0;                                // :235
+    if (T > 1) klat = hp.kl_weight * ((kl0 + kt / (float(T - 1) * B * L) * float(T - 1)) / float(T));   // :229-232
+    out[0] = policy + value + entropy + klat; out[1] = policy; out[2] = value; out[3] = klat; out[4] = entropy;
+    out[5] = mean; out[6] = stdv; out[7] = inv;
+  }
+}
+
+__global__ void __launch_bounds__(256) ppo_grad_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
+                                                       const float* __restrict__ eps, const float* __restrict__ lat_mean,
+                                                       const float* __restrict__ lat_logvar, const float* __restrict__ baseline,
+                                                       const float* __restrict__ vs, const float* __restrict__ logp,
+                                                       const float* __restrict__ behaviour_logp, const float* __restrict__ stats, int T, int B,
+                                                       int A, int L, PpoHyper hp, float* __restrict__ advantages, float* __restrict__ d_logits,
+                                                       float* __restrict__ d_mean, float* __restrict__ d_logvar, float* __restrict__ d_baseline) {
+  const size_t row = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nrow = size_t(T) * B;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrow) return;
+  const float inv_n = 1.f / float(nrow);
+  const float a = (advantages[row] - stats[5]) * stats[7], rho = expf(logp[row] - behaviour_logp[row]);
+  const float clipped = fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon);
+  // d policy_loss / d log-prob: the unclipped branch is the minimum (or both coincide) -> -A rho / N, else 0
+  const float cp = (rho * a <= clipped * a) ? -a * rho * inv_n : 0.f;
+  const float ce = -hp.entropy_cost * inv_n;                        // d entropy_loss / d (row entropy)
+  const float* lg = logits + row * 2 * A;
+  float* dl = d_logits + row * 2 * A;
+  for (int i = lane; i < A; i += 32) {
+    const float loc = lg[i], sr = lg[A + i], scale = softplus(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
+    const float z = (raw - loc) / scale, rs = 1.f / scale;
+    const float dj = -2.f * tanhf(fmaf(scale, e, loc));             // d log_det_tanh(x) / dx
+    const float sig = 1.f / (1.f + expf(-sr));                      // d softplus
+    dl[i] = cp * (z * rs) + ce * dj;
+    dl[A + i] = (cp * ((z * z - 1.f) * rs) + ce * (rs + dj * e)) * sig;
+  }
+  const int t = int(row / B);
+  const float w = hp.kl_weight / (float(T) * float(B) * float(L));  // kl_0 and kl_t both end up with this weight per element
+  const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L, *mn = mu + size_t(B) * L;
+  for (int j = lane; j < L; j += 32) {
+    const float m = mu[j], ev = expf(lv[j]);
+    float gm, gv;
+    if (t == 0) { gm = m; gv = -0.5f * (1.f - ev); }
+    else { gm = -(kArAlpha * mp[j] - m) / kArPriorVar; gv = 0.5f * (ev / kArPriorVar - 1.f); }
+    if (t + 1 < T) gm += kArAlpha * (kArAlpha * m - mn[j]) / kArPriorVar;    // this row's mean is z_{t-1} of the next step's prior
+    d_mean[row * L + j] = w * gm;
+    d_logvar[row * L + j] = w * gv;
+  }
+  __syncwarp();                                                     // every lane has read advantages[row]
+  if (lane == 0) {
+    d_baseline[row] = -0.5f * (vs[row] - baseline[row]) * inv_n;    // d [mean(e^2) / 4] / d baseline
+    advantages[row] = a;
+  }
+}
+
 // Observation-normaliser update (reference masked_running_statistics.py:80-214, called at ppo.py:357-361).  HBM-bound: ONE
 // pass over the [N, D] batch (the reference reads it twice), consecutive threads on consecutive columns (coalesced rows), each
 // block owns a contiguous slab of rows and keeps, per column, sum(x - p) and sum((x - p)^2) about a pivot p = the slab's first
@@ -945,6 +1094,36 @@ int tmjx_gae(const float* truncation, const float* termination, const float* rew
   if (T <= 0 || B <= 0) return pfail(TMJX_E_ARG, "T and B must be positive");
   gae_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(truncation, termination, rewards, values, bootstrap_value, lambda,
                                                                            discount, vs, advantages, T, B);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+/* PPO loss head, see include/tmjx.h.  scratch: 5 T B floats (scaled rewards, termination, row log-prob / entropy / KL). */
+size_t tmjx_ppo_loss_scratch_floats(int T, int B) { return 5 * size_t(T) * size_t(B); }
+int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const float* latent_logvar, const float* baseline,
+                       const float* bootstrap_value, const float* reward, const float* discount, const float* truncation,
+                       const float* raw_action, const float* behaviour_log_prob, const float* eps_entropy, int T, int B, int A, int L,
+                       const TmjxPpoHyper* hyper, float* losses, float* vs, float* advantages, float* d_logits, float* d_latent_mean,
+                       float* d_latent_logvar, float* d_baseline, float* scratch, void* stream) {
+  if (!logits || !latent_mean || !latent_logvar || !baseline || !bootstrap_value || !reward || !discount || !truncation || !raw_action ||
+      !behaviour_log_prob || !eps_entropy || !hyper || !losses || !vs || !advantages || !d_logits || !d_latent_mean || !d_latent_logvar ||
+      !d_baseline || !scratch)
+    return pfail(TMJX_E_ARG, "null argument");
+  if (T <= 0 || B <= 0 || A <= 0 || L <= 0) return pfail(TMJX_E_ARG, "T, B, action and latent sizes must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = size_t(T) * B;
+  float *rewards = scratch, *termination = scratch + n, *logp = scratch + 2 * n, *ent = scratch + 3 * n, *kl = scratch + 4 * n;
+  PpoHyper hp{hyper->entropy_cost, hyper->kl_weight, hyper->discounting, hyper->reward_scaling, hyper->gae_lambda, hyper->clipping_epsilon,
+              hyper->normalize_advantage};
+  const unsigned row_blocks = unsigned((n * 32 + 255) / 256);
+  ppo_prep_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(reward, discount, truncation, hp.reward_scaling, rewards, termination, n);
+  gae_kernel<<<(B + 127) / 128, 128, 0, st>>>(truncation, termination, rewards, baseline, bootstrap_value, hp.gae_lambda, hp.discounting, vs,
+                                              advantages, T, B);
+  ppo_rows_kernel<<<row_blocks, 256, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, T, B, A, L, logp, ent, kl);
+  ppo_reduce_kernel<<<1, 1024, 0, st>>>(advantages, vs, baseline, logp, behaviour_log_prob, ent, kl, T, B, L, hp, losses);
+  ppo_grad_kernel<<<row_blocks, 256, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, logp,
+                                              behaviour_log_prob, losses, T, B, A, L, hp, advantages, d_logits, d_latent_mean,
+                                              d_latent_logvar, d_baseline);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }

@@ -1,4 +1,6 @@
-"""Learner-side pieces that sit next to the acting loop (only GAE is built so far).
+"""Learner-side pieces that sit next to the acting loop: GAE, the observation-normaliser update and the
+PPO loss head (loss terms + the gradients the network backward pass starts from).  The network backward pass, Adam and the
+gradient all-reduce are not built.
 
 `compute_gae` mirrors `track_mjx/agent/mlp_ppo/losses.py:39-101`: same argument names and meaning, time-major `[T, B]` fp32 CUDA
 tensors in, `(vs, advantages)` out, computed by the `tmjx_gae` kernel (csrc/tmjx_policy.cu).  No CPU fallback.
@@ -30,6 +32,51 @@ def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambd
     if rc != 0:
         raise RuntimeError(f"tmjx_gae failed ({rc}): {lib.tmjx_policy_last_error().decode()}")
     return vs, adv
+
+
+class _PpoHyper(C.Structure):
+    _fields_ = [("entropy_cost", C.c_float), ("kl_weight", C.c_float), ("discounting", C.c_float), ("reward_scaling", C.c_float),
+                ("gae_lambda", C.c_float), ("clipping_epsilon", C.c_float), ("normalize_advantage", C.c_int32)]
+
+
+def ppo_loss_head(policy_logits, latent_mean, latent_logvar, baseline, bootstrap_value, reward, discount, truncation, raw_action,
+                  behaviour_log_prob, eps_entropy, entropy_cost: float = 1e-4, kl_weight: float = 1e-3, discounting: float = 0.9,
+                  reward_scaling: float = 1.0, gae_lambda: float = 0.95, clipping_epsilon: float = 0.3, normalize_advantage: bool = True):
+    """`compute_ppo_loss` of `track_mjx/agent/mlp_ppo/losses.py:104-245` from the point where the networks have been applied (same
+    hyper-parameter names and defaults), on time-major `[T, B, ...]` fp32 CUDA tensors (the reference swaps `[B, T]` to
+    time-major itself at :147).  `eps_entropy` is the standard-normal draw the reference takes from `entropy_key`.
+
+    Returns the reference's metrics (`total_loss`, `policy_loss`, `v_loss`, `kl_latent_loss`, `entropy_loss`: 0-d CUDA tensors,
+    views of `losses`), `vs`, `advantages` (normalised when asked) and `d_logits`, `d_latent_mean`, `d_latent_logvar`,
+    `d_baseline` = d total_loss / d input.  One call = five kernel launches (`tmjx_ppo_loss_head`); no CPU fallback."""
+    import torch
+
+    if not policy_logits.is_cuda:
+        raise RuntimeError("ppo_loss_head needs CUDA tensors: there is no CPU fallback")
+    T, B, A2 = policy_logits.shape
+    A, Lz = A2 // 2, latent_mean.shape[-1]
+    cont = lambda a: a.to(torch.float32).contiguous()
+    ins = [cont(a) for a in (policy_logits, latent_mean, latent_logvar, baseline, bootstrap_value, reward, discount, truncation,
+                             raw_action, behaviour_log_prob, eps_entropy)]
+    want = [(T, B, 2 * A), (T, B, Lz), (T, B, Lz), (T, B), (B,), (T, B), (T, B), (T, B), (T, B, A), (T, B), (T, B, A)]
+    for a, w in zip(ins, want):
+        if tuple(a.shape) != w:
+            raise ValueError(f"ppo_loss_head: got shape {tuple(a.shape)}, expected {w}")
+    f = dict(dtype=torch.float32, device=policy_logits.device)
+    lib = L.load()
+    losses, vs, adv = torch.empty(8, **f), torch.empty(T, B, **f), torch.empty(T, B, **f)
+    d_logits, d_mean, d_logvar, d_base = torch.empty_like(ins[0]), torch.empty_like(ins[1]), torch.empty_like(ins[2]), torch.empty(T, B, **f)
+    scratch = torch.empty(int(lib.tmjx_ppo_loss_scratch_floats(T, B)), **f)
+    hp = _PpoHyper(entropy_cost, kl_weight, discounting, reward_scaling, gae_lambda, clipping_epsilon, int(bool(normalize_advantage)))
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.tmjx_ppo_loss_head(*[ptr(a) for a in ins], int(T), int(B), int(A), int(Lz), C.cast(C.byref(hp), C.c_void_p), ptr(losses),
+                                ptr(vs), ptr(adv), ptr(d_logits), ptr(d_mean), ptr(d_logvar), ptr(d_base), ptr(scratch),
+                                C.c_void_p(torch.cuda.current_stream(policy_logits.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"tmjx_ppo_loss_head failed ({rc}): {lib.tmjx_policy_last_error().decode()}")
+    return {"total_loss": losses[0], "policy_loss": losses[1], "v_loss": losses[2], "kl_latent_loss": losses[3], "entropy_loss": losses[4],
+            "kl_weight": kl_weight, "losses": losses, "vs": vs, "advantages": adv, "d_logits": d_logits, "d_latent_mean": d_mean,
+            "d_latent_logvar": d_logvar, "d_baseline": d_base}
 
 
 class RunningStatistics:
