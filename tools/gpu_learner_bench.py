@@ -16,8 +16,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from track_mjx_b200.learner import RunningStatistics, compute_gae, ppo_loss_head  # noqa: E402
 
 
+QUICK = "--quick" in sys.argv        # under ncu: one warm-up, two timed calls
+
+
 def timed(fn, reps=10):
-    for _ in range(3):
+    reps = 2 if QUICK else reps
+    for _ in range(1 if QUICK else 3):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,7 +57,7 @@ def main():
     ms = timed(lambda: ppo_loss_head(logits, mu, lv, v, bv, r, disc, tr, raw, blp, eps), reps=20)
     # every input once (2A + A + A + 2L + 6 floats per row) + every output once (2A + 2L + 3)
     gb = T * B * (4 * A + 2 * Lz + 6 + 2 * A + 2 * Lz + 3) * 4 / 1e9
-    out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 5}
+    out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 6}
     out["peaks"] = {k: peaks.get(k) for k in ("hbm_gbs", "gpu_name")}
     print(json.dumps(out))
 

@@ -558,13 +558,15 @@ __global__ void gae_kernel(const float* __restrict__ truncation, const float* __
 // ---- PPO loss head (reference losses.py:104-245 after the network applications) ---------------------------------------
 // Three passes over the [T, B] rollout, one warp per transition row in the two wide ones (lanes over the 38 actions and the 60
 // latent dimensions, coalesced row reads, xor-shuffle sums: deterministic):
-//   ppo_rows_kernel   target log-prob, entropy and latent-KL row sums                       (reads ~1.3 KB per row, HBM-bound)
-//   ppo_reduce_kernel advantage mean / std, then the five loss terms (one block, fixed summation order, [T B] vectors from L2)
-//   ppo_grad_kernel   d loss / d (logits, latent mean, latent log-variance, baseline) + the normalised advantages
+//   ppo_rows_kernel   target log-prob, entropy and latent-KL row sums + block partials of every mean that needs no normalised
+//                     advantage                                                               (reads ~1.3 KB per row, HBM-bound)
+//   ppo_reduce_kernel stage 1: advantage mean / std, value / entropy / KL terms; stage 2: policy term and total
+//   ppo_grad_kernel   d loss / d (logits, latent mean, latent log-variance, baseline), the normalised advantages and the block
+//                     partials of the clipped surrogate                                   (reads 1.3 KB, writes 0.8 KB per row)
 // The gradients are what a backward pass through the policy / value networks starts from; vs and advantages carry no gradient
 // (stop_gradient at losses.py:100), the bootstrap value therefore gets none.
 struct PpoHyper { float entropy_cost, kl_weight, discounting, reward_scaling, gae_lambda, clipping_epsilon; int normalize_advantage; };
-constexpr float kArAlpha = 0.95f, kArPriorVar = 1.f - 0.95f * 0.95f;   // autoregressive latent prior, losses.py:201-202
+constexpr float kArAlpha = 0.95f, kArPriorVar = 1.f - 0.95f * 0.95f, kArInvPriorVar = 1.f / kArPriorVar;   // autoregressive latent prior, losses.py:201-202
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -580,128 +582,174 @@ __global__ void ppo_prep_kernel(const float* __restrict__ reward, const float* _
   termination[i] = (1.f - discount[i]) * (1.f - truncation[i]);     // :159
 }
 
-__global__ void __launch_bounds__(256) ppo_rows_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
-                                                       const float* __restrict__ eps, const float* __restrict__ lat_mean,
-                                                       const float* __restrict__ lat_logvar, int T, int B, int A, int L,
-                                                       float* __restrict__ logp, float* __restrict__ ent, float* __restrict__ kl) {
-  const size_t row = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nrow = size_t(T) * B;
-  const int lane = threadIdx.x & 31;
-  if (row >= nrow) return;
-  const float* lg = logits + row * 2 * A;
-  float lp = 0.f, en = 0.f;
-  for (int i = lane; i < A; i += 32) {
-    const float loc = lg[i], scale = softplus(lg[A + i]) + 0.001f, raw = raw_action[row * A + i];
-    const float z = (raw - loc) / scale, ls = logf(scale);
-    lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh(raw);
-    en += 0.5f + 0.91893853320467274f + ls + log_det_tanh(fmaf(scale, eps[row * A + i], loc));
+// Grid of the two row kernels: persistent, kPpoBlocks blocks of 8 warps, warp w of the grid takes rows w, w + nwarps, ...; the
+// per-block partial sums (double) are merged by one small block afterwards -- the summation order depends on this constant
+// only, never on the device or the batch
+constexpr int kPpoBlocks = 148 * 8, kPpoWarps = 8, kPpoSums = 6;   // sums: adv, adv^2, entropy, kl_0, kl_t, (vs - baseline)^2
+// Lanes per transition row: with 38 actions a full warp per row idles 26 of 64 lane slots; 8 lanes per row (four rows per warp)
+// use 38 of 40 action slots and 60 of 64 latent slots
+constexpr int kPpoLanes = 8, kPpoRowsPerWarp = 32 / kPpoLanes;
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = kPpoLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void block_partials(double* acc, int nacc, double* __restrict__ partial) {
+  __shared__ double sh[kPpoWarps][kPpoSums];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < nacc; ++k) {                                  // the row-group leaders of the warp hold the sums
+    double v = acc[k];
+#pragma unroll
+    for (int o = kPpoLanes; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][k] = v;
   }
-  const bool first = row < size_t(B);                               // t == 0: standard normal prior, else AR(1) prior
-  const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L;
-  float k = 0.f;
-  for (int j = lane; j < L; j += 32) {
-    const float m = mu[j], v = lv[j];
-    if (first) {
-      k += 1.f + v - m * m - expf(v);                               // * -0.5 below (:206-208)
-    } else {
-      const float dm = kArAlpha * mp[j] - m;
-      k += expf(v) / kArPriorVar + dm * dm / kArPriorVar - 1.f + (logf(kArPriorVar) - v);   // * 0.5 below (:221-226)
+  __syncthreads();
+  if (threadIdx.x < nacc) {
+    double t = 0.0;
+    for (int w = 0; w < kPpoWarps; ++w) t += sh[w][threadIdx.x];
+    partial[size_t(blockIdx.x) * kPpoSums + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kPpoWarps) ppo_rows_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
+                                                       const float* __restrict__ eps, const float* __restrict__ lat_mean,
+                                                       const float* __restrict__ lat_logvar, const float* __restrict__ adv,
+                                                       const float* __restrict__ vs, const float* __restrict__ baseline, int T, int B, int A,
+                                                       int L, float* __restrict__ logp, double* __restrict__ partial) {
+  const size_t nrow = size_t(T) * B, stride = size_t(gridDim.x) * kPpoWarps * kPpoRowsPerWarp;
+  const int lane = threadIdx.x & (kPpoLanes - 1);
+  double acc[kPpoSums] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const float kLogPriorVar = logf(kArPriorVar);
+  // every lane of a warp runs the same number of iterations (the shuffles need all of them); rows past the end are skipped
+  for (size_t row0 = (size_t(blockIdx.x) * kPpoWarps + (threadIdx.x >> 5)) * kPpoRowsPerWarp; row0 < nrow; row0 += stride) {
+    const size_t row = row0 + ((threadIdx.x & 31) / kPpoLanes);
+    const bool live = row < nrow;
+    float lp = 0.f, en = 0.f, k = 0.f;
+    const bool first = row < size_t(B);                             // t == 0: standard normal prior, else AR(1) prior
+    if (live) {
+      const float* lg = logits + row * 2 * A;
+      for (int i = lane; i < A; i += kPpoLanes) {
+        const float loc = lg[i], scale = softplus(lg[A + i]) + 0.001f, raw = raw_action[row * A + i];
+        const float z = (raw - loc) / scale, ls = logf(scale);
+        lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh(raw);
+        en += 0.5f + 0.91893853320467274f + ls + log_det_tanh(fmaf(scale, eps[row * A + i], loc));
+      }
+      const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L;
+      for (int j = lane; j < L; j += kPpoLanes) {
+        const float m = mu[j], v = lv[j];
+        if (first) {
+          k += 1.f + v - m * m - expf(v);                           // * -0.5 below (:206-208)
+        } else {
+          const float dm = kArAlpha * mp[j] - m;
+          k += (expf(v) + dm * dm) * kArInvPriorVar - 1.f + (kLogPriorVar - v);   // * 0.5 below (:221-226)
+        }
+      }
+    }
+    lp = group_sum(lp); en = group_sum(en); k = group_sum(k);
+    if (lane == 0 && live) {
+      logp[row] = lp;
+      const double a = adv[row], e = double(vs[row]) - double(baseline[row]);
+      acc[0] += a; acc[1] += a * a; acc[2] += en;
+      if (first) acc[3] += -0.5 * double(k); else acc[4] += 0.5 * double(k);
+      acc[5] += e * e;
     }
   }
-  lp = warp_sum(lp); en = warp_sum(en); k = warp_sum(k);
-  if (lane == 0) { logp[row] = lp; ent[row] = en; kl[row] = first ? -0.5f * k : 0.5f * k; }
+  block_partials(acc, kPpoSums, partial);
 }
 
-// block-wide sum in a fixed order (thread-sequential, warp xor tree, warps in index order); result valid in every thread
-__device__ float block_sum(float v, float* sh) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int w = 0; w < int(blockDim.x >> 5); ++w) t += sh[w];
-  return t;
-}
-// out: [0] total [1] policy [2] value [3] latent KL [4] entropy loss [5] advantage mean [6] advantage std [7] 1 / (std + 1e-8)
-__global__ void __launch_bounds__(1024) ppo_reduce_kernel(const float* __restrict__ adv, const float* __restrict__ vs,
-                                                          const float* __restrict__ baseline, const float* __restrict__ logp,
-                                                          const float* __restrict__ behaviour_logp, const float* __restrict__ ent,
-                                                          const float* __restrict__ kl, int T, int B, int L, PpoHyper hp,
-                                                          float* __restrict__ out) {
-  __shared__ float sh[32];
-  const size_t n = size_t(T) * B;
-  float mean = 0.f, stdv = 1.f, inv = 1.f;
-  if (hp.normalize_advantage) {                                     // :175-176 (population standard deviation)
-    float s = 0.f;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += adv[i];
-    mean = block_sum(s, sh) / float(n);
-    s = 0.f;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) { const float d = adv[i] - mean; s = fmaf(d, d, s); }
-    stdv = sqrtf(block_sum(s, sh) / float(n));
-    inv = 1.f / (stdv + 1e-8f);
+// out: [0] total [1] policy [2] value [3] latent KL [4] entropy loss [5] advantage mean [6] advantage std [7] 1 / (std + 1e-8).
+// Stage 1 (after ppo_rows_kernel) fills [2..7]; stage 2 (after ppo_grad_kernel, whose partial[.][0] is the surrogate sum) [0..1]
+__global__ void __launch_bounds__(256) ppo_reduce_kernel(const double* __restrict__ partial, int nblk, int stage, int T, int B, int L,
+                                                         PpoHyper hp, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double tot[kPpoSums];
+  const int nsum = stage == 1 ? kPpoSums : 1;
+  for (int k = 0; k < nsum; ++k) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[size_t(b) * kPpoSums + k];
+    __syncthreads();
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (int(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    tot[k] = sh[0];
   }
-  float sp = 0.f, sv = 0.f, se = 0.f, k0 = 0.f, kt = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float a = (adv[i] - mean) * inv, rho = expf(logp[i] - behaviour_logp[i]);                  // :177
-    sp += fminf(rho * a, fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon) * a);   // :179-184
-    const float e = vs[i] - baseline[i];
-    sv = fmaf(e, e, sv);                                            // :187-188
-    se += ent[i];
-    if (i < size_t(B)) k0 += kl[i]; else kt += kl[i];
-  }
-  sp = block_sum(sp, sh); sv = block_sum(sv, sh); se = block_sum(se, sh); k0 = block_sum(k0, sh); kt = block_sum(kt, sh);
-  if (threadIdx.x == 0) {
-    const float policy = -sp / float(n), value = sv / float(n) * 0.5f * 0.5f, entropy = hp.entropy_cost * -(se / float(n));
-    const float kl0 = k0 / (float(B) * L);
+  if (threadIdx.x != 0) return;
+  const double n = double(T) * B;
+  if (stage == 1) {
+    float mean = 0.f, stdv = 1.f, inv = 1.f;
+    if (hp.normalize_advantage) {                                   // :175-176 (population standard deviation)
+      const double m = tot[0] / n;
+      mean = float(m);
+      stdv = float(sqrt(fmax(tot[1] / n - m * m, 0.0)));
+      inv = 1.f / (stdv + 1e-8f);
+    }
+    const float kl0 = float(tot[3] / (double(B) * L));
     float klat = hp.kl_weight * kl0;                                // :235
-    if (T > 1) klat = hp.kl_weight * ((kl0 + kt / (float(T - 1) * B * L) * float(T - 1)) / float(T));   // :229-232
-    out[0] = policy + value + entropy + klat; out[1] = policy; out[2] = value; out[3] = klat; out[4] = entropy;
+    if (T > 1) klat = hp.kl_weight * ((kl0 + float(tot[4] / (double(T - 1) * B * L)) * float(T - 1)) / float(T));   // :229-232
+    out[2] = float(tot[5] / n) * 0.5f * 0.5f;                       // :187-188
+    out[3] = klat;
+    out[4] = hp.entropy_cost * -float(tot[2] / n);                  // :191-194
     out[5] = mean; out[6] = stdv; out[7] = inv;
+  } else {
+    out[1] = -float(tot[0] / n);                                    // :184
+    out[0] = out[1] + out[2] + out[4] + out[3];                     // :237
   }
 }
 
-__global__ void __launch_bounds__(256) ppo_grad_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
+__global__ void __launch_bounds__(32 * kPpoWarps) ppo_grad_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
                                                        const float* __restrict__ eps, const float* __restrict__ lat_mean,
                                                        const float* __restrict__ lat_logvar, const float* __restrict__ baseline,
                                                        const float* __restrict__ vs, const float* __restrict__ logp,
                                                        const float* __restrict__ behaviour_logp, const float* __restrict__ stats, int T, int B,
-                                                       int A, int L, PpoHyper hp, float* __restrict__ advantages, float* __restrict__ d_logits,
-                                                       float* __restrict__ d_mean, float* __restrict__ d_logvar, float* __restrict__ d_baseline) {
-  const size_t row = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nrow = size_t(T) * B;
-  const int lane = threadIdx.x & 31;
-  if (row >= nrow) return;
-  const float inv_n = 1.f / float(nrow);
-  const float a = (advantages[row] - stats[5]) * stats[7], rho = expf(logp[row] - behaviour_logp[row]);
-  const float clipped = fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon);
-  // d policy_loss / d log-prob: the unclipped branch is the minimum (or both coincide) -> -A rho / N, else 0
-  const float cp = (rho * a <= clipped * a) ? -a * rho * inv_n : 0.f;
+                                                       int A, int L, PpoHyper hp, const float* __restrict__ adv_raw, float* __restrict__ advantages,
+                                                       float* __restrict__ d_logits,
+                                                       float* __restrict__ d_mean, float* __restrict__ d_logvar, float* __restrict__ d_baseline,
+                                                       double* __restrict__ partial) {
+  const size_t nrow = size_t(T) * B, stride = size_t(gridDim.x) * kPpoWarps * kPpoRowsPerWarp;
+  const int lane = threadIdx.x & (kPpoLanes - 1);
+  const float inv_n = 1.f / float(nrow), adv_mean = stats[5], adv_inv = stats[7];
   const float ce = -hp.entropy_cost * inv_n;                        // d entropy_loss / d (row entropy)
-  const float* lg = logits + row * 2 * A;
-  float* dl = d_logits + row * 2 * A;
-  for (int i = lane; i < A; i += 32) {
-    const float loc = lg[i], sr = lg[A + i], scale = softplus(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
-    const float z = (raw - loc) / scale, rs = 1.f / scale;
-    const float dj = -2.f * tanhf(fmaf(scale, e, loc));             // d log_det_tanh(x) / dx
-    const float sig = 1.f / (1.f + expf(-sr));                      // d softplus
-    dl[i] = cp * (z * rs) + ce * dj;
-    dl[A + i] = (cp * ((z * z - 1.f) * rs) + ce * (rs + dj * e)) * sig;
-  }
-  const int t = int(row / B);
   const float w = hp.kl_weight / (float(T) * float(B) * float(L));  // kl_0 and kl_t both end up with this weight per element
-  const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L, *mn = mu + size_t(B) * L;
-  for (int j = lane; j < L; j += 32) {
-    const float m = mu[j], ev = expf(lv[j]);
-    float gm, gv;
-    if (t == 0) { gm = m; gv = -0.5f * (1.f - ev); }
-    else { gm = -(kArAlpha * mp[j] - m) / kArPriorVar; gv = 0.5f * (ev / kArPriorVar - 1.f); }
-    if (t + 1 < T) gm += kArAlpha * (kArAlpha * m - mn[j]) / kArPriorVar;    // this row's mean is z_{t-1} of the next step's prior
-    d_mean[row * L + j] = w * gm;
-    d_logvar[row * L + j] = w * gv;
+  double acc[1] = {0.0};
+  for (size_t row0 = (size_t(blockIdx.x) * kPpoWarps + (threadIdx.x >> 5)) * kPpoRowsPerWarp; row0 < nrow; row0 += stride) {
+    const size_t row = row0 + ((threadIdx.x & 31) / kPpoLanes);
+    if (row >= nrow) continue;                                      // no warp-wide operation below
+    const float a = (adv_raw[row] - adv_mean) * adv_inv, rho = expf(logp[row] - behaviour_logp[row]);   // :177
+    const float clipped = fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon);
+    const float s1 = rho * a, s2 = clipped * a;                     // :179-182
+    // d policy_loss / d log-prob: the unclipped branch is the minimum (or both coincide) -> -A rho / N, else 0
+    const float cp = (s1 <= s2) ? -a * rho * inv_n : 0.f;
+    const float* lg = logits + row * 2 * A;
+    float* dl = d_logits + row * 2 * A;
+    for (int i = lane; i < A; i += kPpoLanes) {
+      const float loc = lg[i], sr = lg[A + i], scale = softplus(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
+      const float z = (raw - loc) / scale, rs = 1.f / scale;
+      const float dj = -2.f * tanhf(fmaf(scale, e, loc));           // d log_det_tanh(x) / dx
+      const float sig = 1.f / (1.f + expf(-sr));                    // d softplus
+      dl[i] = cp * (z * rs) + ce * dj;
+      dl[A + i] = (cp * ((z * z - 1.f) * rs) + ce * (rs + dj * e)) * sig;
+    }
+    const int t = int(row / B);
+    const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L, *mn = mu + size_t(B) * L;
+    for (int j = lane; j < L; j += kPpoLanes) {
+      const float m = mu[j], ev = expf(lv[j]);
+      float gm, gv;
+      if (t == 0) { gm = m; gv = -0.5f * (1.f - ev); }
+      else { gm = -(kArAlpha * mp[j] - m) * kArInvPriorVar; gv = 0.5f * (ev * kArInvPriorVar - 1.f); }
+      if (t + 1 < T) gm += kArAlpha * (kArAlpha * m - mn[j]) * kArInvPriorVar;   // this row's mean is z_{t-1} of the next step's prior
+      d_mean[row * L + j] = w * gm;
+      d_logvar[row * L + j] = w * gv;
+    }
+    if (lane == 0) {
+      d_baseline[row] = -0.5f * (vs[row] - baseline[row]) * inv_n;  // d [mean(e^2) / 4] / d baseline
+      advantages[row] = a;
+      acc[0] += double(fminf(s1, s2));
+    }
   }
-  __syncwarp();                                                     // every lane has read advantages[row]
-  if (lane == 0) {
-    d_baseline[row] = -0.5f * (vs[row] - baseline[row]) * inv_n;    // d [mean(e^2) / 4] / d baseline
-    advantages[row] = a;
-  }
+  block_partials(acc, 1, partial);
 }
 
 // Observation-normaliser update (reference masked_running_statistics.py:80-214, called at ppo.py:357-361).  HBM-bound: ONE
@@ -788,25 +836,40 @@ __global__ void __launch_bounds__(kStatTx* kStatTy) stats_partial_vec_kernel(con
                           fmaxf(s2.w - dm.w * s1.w, 0.f));
   }
 }
-// Fixed-order merge of the slab moments; out[0..D) = sum(x - mean) = N (xbar - mean), out[D..2D) = xbar, out[2D..3D) = M2
-__global__ void stats_combine_kernel(const float* __restrict__ partial, int N, int nblk, int D, const float* __restrict__ mean,
-                                     float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Merge of the slab moments, one warp per column: lane l merges slabs l, l + 32, ... in order (its loads are independent of
+// the merge chain, so they are all in flight at once), then a five-step xor tree merges the lanes -- a fixed order for a given
+// slab count.  out[0..D) = sum(x - mean) = N (xbar - mean), out[D..2D) = xbar, out[2D..3D) = M2
+__device__ __forceinline__ void moments_merge(float& n, float& mu, float& m2, float nb, float mb, float qb) {
+  if (nb == 0.f) return;
+  if (n == 0.f) { n = nb; mu = mb; m2 = qb; return; }
+  const float nt = n + nb, delta = mb - mu;
+  mu += delta * (nb / nt);
+  m2 += qb + delta * delta * (n * nb / nt);
+  n = nt;
+}
+__global__ void __launch_bounds__(256) stats_combine_kernel(const float* __restrict__ partial, int N, int nblk, int D,
+                                                            const float* __restrict__ mean, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= D) return;
   const int rows_per_block = (N + nblk - 1) / nblk;
   float n = 0.f, mu = 0.f, m2 = 0.f;
-  for (int b = 0; b < nblk; ++b) {
+#pragma unroll 4
+  for (int b = lane; b < nblk; b += 32) {
     const int r0 = b * rows_per_block, r1 = min(N, r0 + rows_per_block);
-    if (r0 >= r1) break;
-    const float nb = float(r1 - r0), mb = partial[(size_t(b) * 2) * D + c], qb = partial[(size_t(b) * 2 + 1) * D + c];
-    const float nt = n + nb, delta = mb - mu;
-    mu += delta * (nb / nt);
-    m2 += qb + delta * delta * (n * nb / nt);
-    n = nt;
+    if (r0 < r1) moments_merge(n, mu, m2, float(r1 - r0), partial[(size_t(b) * 2) * D + c], partial[(size_t(b) * 2 + 1) * D + c]);
   }
-  out[c] = n * (mu - mean[c]);
-  out[D + c] = mu;
-  out[2 * D + c] = m2;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mu, o), qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    // both partners must end up with the same bits: the lower lane's moments are always the left operand
+    if (lane & o) { float n2 = nb, mu2 = mb, q2 = qb; moments_merge(n2, mu2, q2, n, mu, m2); n = n2; mu = mu2; m2 = q2; }
+    else moments_merge(n, mu, m2, nb, mb, qb);
+  }
+  if (lane == 0) {
+    out[c] = n * (mu - mean[c]);
+    out[D + c] = mu;
+    out[2 * D + c] = m2;
+  }
 }
 // After sum(x - mean) [D] and the row count were summed over the GPUs: new count (to a side cell), mean update in place and this
 // GPU's share of the variance update, left where sum(x - mean) was.  With d = xbar_local - m, g = S1 / N_total (global batch
@@ -1098,8 +1161,9 @@ int tmjx_gae(const float* truncation, const float* termination, const float* rew
   return TMJX_OK;
 }
 
-/* PPO loss head, see include/tmjx.h.  scratch: 5 T B floats (scaled rewards, termination, row log-prob / entropy / KL). */
-size_t tmjx_ppo_loss_scratch_floats(int T, int B) { return 5 * size_t(T) * size_t(B); }
+/* PPO loss head, see include/tmjx.h.  scratch: block partial sums (double), then 4 T B floats (scaled rewards, termination, row
+ * log-prob, advantages before normalisation). */
+size_t tmjx_ppo_loss_scratch_floats(int T, int B) { return 2 * size_t(kPpoBlocks) * kPpoSums + 4 * size_t(T) * size_t(B); }
 int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const float* latent_logvar, const float* baseline,
                        const float* bootstrap_value, const float* reward, const float* discount, const float* truncation,
                        const float* raw_action, const float* behaviour_log_prob, const float* eps_entropy, int T, int B, int A, int L,
@@ -1110,20 +1174,25 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
       !d_baseline || !scratch)
     return pfail(TMJX_E_ARG, "null argument");
   if (T <= 0 || B <= 0 || A <= 0 || L <= 0) return pfail(TMJX_E_ARG, "T, B, action and latent sizes must be positive");
+  if (reinterpret_cast<uintptr_t>(scratch) % 8 != 0) return pfail(TMJX_E_ARG, "scratch must be 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = size_t(T) * B;
-  float *rewards = scratch, *termination = scratch + n, *logp = scratch + 2 * n, *ent = scratch + 3 * n, *kl = scratch + 4 * n;
+  double* partial = reinterpret_cast<double*>(scratch);
+  float *rewards = scratch + 2 * size_t(kPpoBlocks) * kPpoSums, *termination = rewards + n, *logp = rewards + 2 * n, *adv_raw = rewards + 3 * n;
   PpoHyper hp{hyper->entropy_cost, hyper->kl_weight, hyper->discounting, hyper->reward_scaling, hyper->gae_lambda, hyper->clipping_epsilon,
               hyper->normalize_advantage};
-  const unsigned row_blocks = unsigned((n * 32 + 255) / 256);
+  const size_t rows_per_block = size_t(kPpoWarps) * kPpoRowsPerWarp;
+  const int nblk = int(std::min<size_t>(kPpoBlocks, (n + rows_per_block - 1) / rows_per_block));
   ppo_prep_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(reward, discount, truncation, hp.reward_scaling, rewards, termination, n);
   gae_kernel<<<(B + 127) / 128, 128, 0, st>>>(truncation, termination, rewards, baseline, bootstrap_value, hp.gae_lambda, hp.discounting, vs,
-                                              advantages, T, B);
-  ppo_rows_kernel<<<row_blocks, 256, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, T, B, A, L, logp, ent, kl);
-  ppo_reduce_kernel<<<1, 1024, 0, st>>>(advantages, vs, baseline, logp, behaviour_log_prob, ent, kl, T, B, L, hp, losses);
-  ppo_grad_kernel<<<row_blocks, 256, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, logp,
-                                              behaviour_log_prob, losses, T, B, A, L, hp, advantages, d_logits, d_latent_mean,
-                                              d_latent_logvar, d_baseline);
+                                              adv_raw, T, B);
+  ppo_rows_kernel<<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, adv_raw, vs, baseline, T, B,
+                                                    A, L, logp, partial);
+  ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, T, B, L, hp, losses);
+  ppo_grad_kernel<<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, logp,
+                                                    behaviour_log_prob, losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean,
+                                                    d_latent_logvar, d_baseline, partial);
+  ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 2, T, B, L, hp, losses);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }
@@ -1142,7 +1211,7 @@ int tmjx_running_stats_sums(const float* batch, int N, int D, const float* mean,
   } else {
     stats_partial_kernel<<<nblk, kStatThreads, 0, st>>>(batch, N, D, scratch);
   }
-  stats_combine_kernel<<<(D + 255) / 256, 256, 0, st>>>(scratch, N, nblk, D, mean, sums);
+  stats_combine_kernel<<<(D * 32 + 255) / 256, 256, 0, st>>>(scratch, N, nblk, D, mean, sums);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }
