@@ -270,6 +270,17 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
                        const TmjxPpoHyper* hyper, float* losses, float* vs, float* advantages, float* d_logits, float* d_latent_mean,
                        float* d_latent_logvar, float* d_baseline, float* scratch, void* stream);
 
+/* Optimiser step on flat fp32 DEVICE buffers of n elements (parameters, gradients, Adam moments mu / nu).  Replaces the update of
+ *   optax.chain(optax.clip_by_global_norm(10.0), optax.adam(learning_rate))   reference track_mjx/agent/mlp_ppo/ppo.py:517-520
+ * (optax 0.2.5, not vendored): g = grads * grad_scale (1 / world_size after a SUM all-reduce = the reference's pmean);
+ * if max_grad_norm > 0 and not ||g|| < max_grad_norm: g = (g / ||g||) * max_grad_norm; mu = b1 mu + (1 - b1) g;
+ * nu = b2 nu + (1 - b2) g^2; params += -lr (mu / (1 - b1^count)) / (sqrt(nu / (1 - b2^count)) + eps).  count = the 1-based
+ * step number (optax's count after its increment).  grad_norm_out (device, one float, may be NULL) receives ||g|| before
+ * clipping.  scratch >= tmjx_adam_scratch_floats() floats, 8-byte aligned.  Deterministic. */
+size_t tmjx_adam_scratch_floats(void);
+int tmjx_adam_step(float* params, const float* grads, float* mu, float* nu, size_t n, float learning_rate, float b1, float b2, float eps,
+                   float max_grad_norm, float grad_scale, int count, float* grad_norm_out, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from track_mjx_b200.learner import RunningStatistics, compute_gae, ppo_loss_head  # noqa: E402
+from track_mjx_b200.learner import Adam, RunningStatistics, compute_gae, ppo_loss_head  # noqa: E402
 
 
 QUICK = "--quick" in sys.argv        # under ncu: one warm-up, two timed calls
@@ -58,6 +58,16 @@ def main():
     # every input once (2A + A + A + 2L + 6 floats per row) + every output once (2A + 2L + 3)
     gb = T * B * (4 * A + 2 * Lz + 6 + 2 * A + 2 * Lz + 3) * 4 / 1e9
     out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 6}
+    # optimiser step over the intention network's parameter count (2.6 M: L2-resident) and over 256 Mi parameters (HBM-bound)
+    for name, n in (("adam_2p6M", 2_600_000), ("adam_256M", 1 << 28)):
+        if QUICK and n > 1 << 24:
+            continue
+        prm, grd = torch.zeros(n, device="cuda"), torch.randn(n, device="cuda")
+        o = Adam(prm)
+        ms = timed(lambda: o.step(grd), reps=20)
+        gb = n * 32 / 1e9          # g twice (norm pass + update), p / mu / nu read and written
+        out[name] = {"n": n, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 2}
+        del prm, grd, o
     out["peaks"] = {k: peaks.get(k) for k in ("hbm_gbs", "gpu_name")}
     print(json.dumps(out))
 

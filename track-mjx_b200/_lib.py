@@ -129,6 +129,9 @@ def load() -> C.CDLL:
     lib.tmjx_ppo_loss_scratch_floats.argtypes = [i32, i32]
     lib.tmjx_ppo_loss_scratch_floats.restype = sz
     lib.tmjx_ppo_loss_head.argtypes = [vp] * 11 + [i32] * 4 + [vp] * 10
+    lib.tmjx_adam_scratch_floats.argtypes = []
+    lib.tmjx_adam_scratch_floats.restype = sz
+    lib.tmjx_adam_step.argtypes = [vp, vp, vp, vp, sz] + [C.c_float] * 6 + [i32, vp, vp, vp]
     lib.tmjx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, vp]
     if lib.tmjx_abi_version() != 1:
         raise ImportError("libtmjx.so ABI version mismatch")

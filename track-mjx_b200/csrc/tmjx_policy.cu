@@ -752,6 +752,78 @@ __global__ void __launch_bounds__(32 * kPpoWarps) ppo_grad_kernel(const float* _
   block_partials(acc, 1, partial);
 }
 
+// ---- Optimiser step (reference ppo.py:517-520: optax.chain(clip_by_global_norm(10.0), adam(lr)), optax 0.2.5) -------------
+// Flat fp32 buffers (parameters, gradients, first and second moments), 16-byte accesses over the aligned body.  Two launches:
+// block partial sums of g^2 (double, fixed order), then the update, every block re-reducing the kAdamBlocks partials for the
+// global norm (1184 doubles from L2, cheaper than a third launch).  28 B per parameter + 4 B for the norm pass; at the
+// intention network's 2.6 M parameters all of it is L2-resident and the step is launch-latency bound.
+constexpr int kAdamBlocks = 148 * 8, kAdamThreads = 256;
+__global__ void __launch_bounds__(kAdamThreads) sumsq_partial_kernel(const float* __restrict__ g, size_t n, float grad_scale,
+                                                                    double* __restrict__ partial) {
+  __shared__ double sh[kAdamThreads / 32];
+  double acc = 0.0;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nthr = size_t(gridDim.x) * blockDim.x;
+  const size_t n4 = (reinterpret_cast<uintptr_t>(g) % 16 == 0) ? n / 4 : 0;
+  for (size_t i = tid; i < n4; i += nthr) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float a = v.x * grad_scale, b = v.y * grad_scale, c = v.z * grad_scale, d = v.w * grad_scale;
+    acc += (double(a) * double(a) + double(b) * double(b)) + (double(c) * double(c) + double(d) * double(d));
+  }
+  for (size_t i = 4 * n4 + tid; i < n; i += nthr) {
+    const float v = g[i] * grad_scale;
+    acc += double(v) * double(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kAdamThreads / 32; ++w) t += sh[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(kAdamThreads) adam_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
+                                                                 float* __restrict__ nu, size_t n, float lr, float b1, float b2, float eps,
+                                                                 float max_norm, float grad_scale, int count, const double* __restrict__ partial,
+                                                                 int npartial, float* __restrict__ norm_out) {
+  __shared__ double sh[kAdamThreads];
+  __shared__ float s_norm;
+  if (max_norm > 0.f || norm_out) {
+    double t = 0.0;
+    for (int b = threadIdx.x; b < npartial; b += blockDim.x) t += partial[b];
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = kAdamThreads / 2; o > 0; o >>= 1) {
+      if (int(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { s_norm = float(sqrt(sh[0])); if (norm_out && blockIdx.x == 0) norm_out[0] = s_norm; }
+    __syncthreads();
+  }
+  const float g_norm = (max_norm > 0.f) ? s_norm : 0.f;
+  const bool clip = max_norm > 0.f && !(g_norm < max_norm);          // optax: select(g_norm < max_norm, g, (g / g_norm) * max_norm)
+  const float c1 = 1.f - powf(b1, float(count)), c2 = 1.f - powf(b2, float(count));   // bias corrections, count after increment
+  auto elem = [&](float gi, float& pi, float& mi, float& vi) {
+    gi *= grad_scale;
+    if (clip) gi = (gi / g_norm) * max_norm;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * (gi * gi);
+    pi = pi + (-lr) * ((mi / c1) / (sqrtf(vi / c2) + eps));
+  };
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nthr = size_t(gridDim.x) * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mu) |
+                         reinterpret_cast<uintptr_t>(nu)) % 16) == 0;
+  const size_t n4 = aligned ? n / 4 : 0;
+  for (size_t i = tid; i < n4; i += nthr) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(mu)[i], v4 = reinterpret_cast<float4*>(nu)[i];
+    elem(g4.x, p4.x, m4.x, v4.x); elem(g4.y, p4.y, m4.y, v4.y); elem(g4.z, p4.z, m4.z, v4.z); elem(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(mu)[i] = m4; reinterpret_cast<float4*>(nu)[i] = v4;
+  }
+  for (size_t i = 4 * n4 + tid; i < n; i += nthr) elem(g[i], p[i], mu[i], nu[i]);
+}
+
 // Observation-normaliser update (reference masked_running_statistics.py:80-214, called at ppo.py:357-361).  HBM-bound: ONE
 // pass over the [N, D] batch (the reference reads it twice), consecutive threads on consecutive columns (coalesced rows), each
 // block owns a contiguous slab of rows and keeps, per column, sum(x - p) and sum((x - p)^2) about a pivot p = the slab's first
@@ -1193,6 +1265,23 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
                                                     behaviour_log_prob, losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean,
                                                     d_latent_logvar, d_baseline, partial);
   ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 2, T, B, L, hp, losses);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+/* Optimiser step, see include/tmjx.h. */
+size_t tmjx_adam_scratch_floats(void) { return 2 * size_t(kAdamBlocks); }
+int tmjx_adam_step(float* params, const float* grads, float* mu, float* nu, size_t n, float learning_rate, float b1, float b2, float eps,
+                   float max_grad_norm, float grad_scale, int count, float* grad_norm_out, float* scratch, void* stream) {
+  if (!params || !grads || !mu || !nu || !scratch) return pfail(TMJX_E_ARG, "null argument");
+  if (n == 0 || count <= 0) return pfail(TMJX_E_ARG, "n and count (the 1-based step number) must be positive");
+  if (reinterpret_cast<uintptr_t>(scratch) % 8 != 0) return pfail(TMJX_E_ARG, "scratch must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = int(std::min<size_t>(kAdamBlocks, (n + kAdamThreads - 1) / kAdamThreads));
+  double* partial = reinterpret_cast<double*>(scratch);
+  if (max_grad_norm > 0.f || grad_norm_out) sumsq_partial_kernel<<<nblk, kAdamThreads, 0, st>>>(grads, n, grad_scale, partial);
+  adam_apply_kernel<<<nblk, kAdamThreads, 0, st>>>(params, grads, mu, nu, n, learning_rate, b1, b2, eps, max_grad_norm, grad_scale, count,
+                                                   partial, nblk, grad_norm_out);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }

@@ -1,6 +1,6 @@
 """Learner-side pieces that sit next to the acting loop: GAE, the observation-normaliser update and the
-PPO loss head (loss terms + the gradients the network backward pass starts from).  The network backward pass, Adam and the
-gradient all-reduce are not built.
+PPO loss head (loss terms + the gradients the network backward pass starts from), the KL-weight schedule and the optimiser step
+(global-norm clip + Adam, gradient all-reduce).  The backward pass through the networks is not built.
 
 `compute_gae` mirrors `track_mjx/agent/mlp_ppo/losses.py:39-101`: same argument names and meaning, time-major `[T, B]` fp32 CUDA
 tensors in, `(vs, advantages)` out, computed by the `tmjx_gae` kernel (csrc/tmjx_policy.cu).  No CPU fallback.
@@ -77,6 +77,71 @@ def ppo_loss_head(policy_logits, latent_mean, latent_logvar, baseline, bootstrap
     return {"total_loss": losses[0], "policy_loss": losses[1], "v_loss": losses[2], "kl_latent_loss": losses[3], "entropy_loss": losses[4],
             "kl_weight": kl_weight, "losses": losses, "vs": vs, "advantages": adv, "d_logits": d_logits, "d_latent_mean": d_mean,
             "d_latent_logvar": d_logvar, "d_baseline": d_base}
+
+
+def create_ramp_schedule(max_value: float = 0.1, min_value: float = 0.0001, ramp_steps: int = 1000, warmup_steps: int = 0,
+                         schedule: str = "linear", period: int = 45):
+    """KL-weight schedule of `track_mjx/agent/mlp_ppo/losses.py:248-290` (host arithmetic, float32 like the reference; its quirks
+    kept: the linear progress is clipped below at `min_value`, not 0, and the cyclic forms add `min_value` to the midpoint)."""
+    import numpy as np
+
+    f = np.float32
+    if schedule not in ("linear", "cosine", "sine"):
+        raise ValueError(f"schedule must be either 'linear' 'cosine', or 'sine', not {schedule}")
+
+    def schedule_fn(step):
+        step = f(step)
+        if schedule == "linear":
+            progress = np.clip((step - f(warmup_steps)) / f(ramp_steps), f(min_value), f(1))
+            return f(min_value) if step < warmup_steps else f(progress * f(max_value))
+        amplitude, midpoint = f((max_value - min_value) / 2), f((max_value + min_value) / 2)
+        angle = (f(2 * np.pi) * step) / f(period)
+        if schedule == "cosine":
+            return f(midpoint + f(min_value) + amplitude * np.cos(angle, dtype=f))
+        return f(midpoint + f(min_value) + amplitude * np.sin(angle - f(np.pi / 2), dtype=f))
+
+    return schedule_fn
+
+
+class Adam:
+    """`optax.chain(optax.clip_by_global_norm(max_grad_norm), optax.adam(learning_rate))` of `ppo.py:517-520` on one flat fp32
+    CUDA parameter buffer (`tmjx_adam_step`).  `step(grads)` updates `params` in place; with an initialised `torch.distributed`
+    group the gradients are SUM all-reduced (NCCL) first and scaled by 1 / world_size inside the kernel, which is the reference's
+    `jax.lax.pmean(grads)` (brax `gradients.py`, called at ppo.py:371-376).  No CPU fallback."""
+
+    def __init__(self, params, learning_rate: float = 1e-4, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8,
+                 max_grad_norm: float = 10.0):
+        import torch
+
+        if not params.is_cuda or params.dtype != torch.float32 or not params.is_contiguous():
+            raise RuntimeError("Adam needs a contiguous float32 CUDA parameter buffer: there is no CPU fallback")
+        self.torch, self.lib, self.params = torch, L.load(), params
+        self.mu, self.nu = torch.zeros_like(params), torch.zeros_like(params)
+        self.count = 0
+        self.hp = (float(learning_rate), float(b1), float(b2), float(eps), float(max_grad_norm))
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=params.device)
+        self._scratch = torch.zeros(int(self.lib.tmjx_adam_scratch_floats()), dtype=torch.float32, device=params.device)
+
+    def step(self, grads, all_reduce: bool | None = None):
+        t = self.torch
+        if grads.shape != self.params.shape or grads.dtype != t.float32 or not grads.is_cuda:
+            raise ValueError("grads must be a float32 CUDA tensor shaped like params")
+        grads = grads.contiguous()
+        dist = t.distributed
+        if all_reduce is None:
+            all_reduce = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        scale = 1.0
+        if all_reduce:
+            dist.all_reduce(grads)
+            scale = 1.0 / dist.get_world_size()
+        self.count += 1
+        ptr = lambda a: C.c_void_p(a.data_ptr())
+        rc = self.lib.tmjx_adam_step(ptr(self.params), ptr(grads), ptr(self.mu), ptr(self.nu), self.params.numel(), *self.hp, scale,
+                                     self.count, ptr(self.grad_norm), ptr(self._scratch),
+                                     C.c_void_p(t.cuda.current_stream(self.params.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_adam_step failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+        return self.params
 
 
 class RunningStatistics:
