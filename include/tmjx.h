@@ -223,6 +223,20 @@ int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_late
 int tmjx_policy_linear(const TmjxPolicy* p, int which, const float* x, int ldx, float* y, int ldy, int n_env, void* stream);
 int tmjx_policy_launches_per_act(const TmjxPolicy* p);
 
+/* Value network forward (the baseline / bootstrap value of the PPO loss).  Replaces
+ *   networks.make_value_network(...).apply   as built at reference track_mjx/agent/mlp_ppo/ppo_networks.py:180-185 and called at
+ *                                            losses.py:151-155 (brax 0.12.3 training/networks.py: normalise, MLP with swish on every
+ *                                            layer but the last, Dense to 1, squeeze)
+ * on the same tcgen05 TF32 GEMM as the policy.  `params`: ONE host fp32 vector: normaliser mean[obs], std[obs]; per hidden layer W
+ * [in, out] row-major, b; output W [., 1], b[1].  obs [n_env, obs_size] and value [n_env] are DEVICE pointers.  The object is
+ * released with tmjx_policy_destroy. */
+typedef struct TmjxValueDesc {
+  int32_t obs_size, n_hidden_layers, hidden_layers[TMJX_POLICY_MAX_LAYERS];
+} TmjxValueDesc;
+size_t tmjx_value_param_count(const TmjxValueDesc* d);
+int tmjx_value_create(const TmjxValueDesc* d, const float* params, size_t n_params, int device, int max_env, TmjxPolicy** out);
+int tmjx_value_apply(const TmjxPolicy* v, const float* obs, float* value, int n_env, void* stream);
+
 /* Generalised Advantage Estimation over a rollout (first piece of the learner side).  Replaces
  *   compute_gae   reference track_mjx/agent/mlp_ppo/losses.py:39-101
  * All arrays are DEVICE pointers, time-major [T, B] fp32 (bootstrap_value [B]); outputs vs and advantages [T, B].  Same

@@ -196,3 +196,45 @@ def test_older_gemm_kernels_agree_with_the_tma_kernel(setup, variant, monkeypatc
     torch.cuda.synchronize()
     assert (y1 - y0).abs().max().item() < 1e-5
     alt.close()
+
+
+@pytest.mark.gpu
+def test_value_network_matches_fp32_reference_and_feeds_the_loss_head():
+    """`ValueNetwork.apply` (normalise, Dense + swish x 2, Dense to 1 on the TF32 tensor-core GEMM) against a float64 torch
+    evaluation of the same MLP: 1e-2 absolute on O(1) values (TF32 operand truncation over K = 696 / 1024 / 1024, the bound of the
+    single-layer test above accumulated over three layers).  Then the learner chain on a small rollout: baseline / bootstrap from the
+    value network -> `ppo_loss_head` -> finite loss terms and gradient seeds of the right shapes."""
+    import torch
+
+    from track_mjx_b200.learner import ppo_loss_head
+    from track_mjx_b200.policy import ValueNetwork, init_value_params
+
+    rng = np.random.default_rng(3)
+    obs_size, T, B, A, Lz = 696, 5, 300, 38, 60
+    params = init_value_params(obs_size, (1024, 1024), seed=1)
+    params["norm/mean"] = rng.normal(0, 0.5, obs_size).astype(np.float32)
+    params["norm/std"] = rng.uniform(0.5, 2.0, obs_size).astype(np.float32)
+    for i in range(3):
+        params[f"hidden_{i}/bias"] = rng.normal(0, 0.1, params[f"hidden_{i}/bias"].shape).astype(np.float32)
+    net = ValueNetwork(obs_size, params, max_env=1024)           # 1500 rows -> two chunks
+    obs = torch.from_numpy((rng.normal(size=(T, B, obs_size)) * 1.5 + 0.3).astype(np.float32)).cuda()
+    got = net.apply(obs)
+    torch.cuda.synchronize()
+    assert got.shape == (T, B)
+    x = (obs.double().cpu() - torch.from_numpy(params["norm/mean"]).double()) / torch.from_numpy(params["norm/std"]).double()
+    for i in range(3):
+        x = x @ torch.from_numpy(params[f"hidden_{i}/kernel"]).double() + torch.from_numpy(params[f"hidden_{i}/bias"]).double()
+        if i < 2:
+            x = torch.nn.functional.silu(x)
+    want = x.squeeze(-1)
+    err = (got.double().cpu() - want).abs().max().item()
+    assert want.abs().max().item() > 0.3 and err < 1e-2, (err, want.abs().max().item())
+    boot = net.apply(obs[-1])
+    assert torch.equal(boot, got[-1])                            # same rows, same kernel: bitwise
+    g = lambda *s: torch.from_numpy(rng.normal(size=s).astype(np.float32)).cuda()
+    out = ppo_loss_head(g(T, B, 2 * A) * 0.5, g(T, B, Lz), g(T, B, Lz) * 0.5 - 1, got, boot, g(T, B), torch.ones(T, B, device="cuda"),
+                        torch.zeros(T, B, device="cuda"), g(T, B, A), g(T, B) - 40, g(T, B, A))
+    torch.cuda.synchronize()
+    assert all(np.isfinite(float(out[k])) for k in ("total_loss", "policy_loss", "v_loss", "kl_latent_loss", "entropy_loss"))
+    assert out["d_baseline"].shape == (T, B) and out["d_logits"].shape == (T, B, 2 * A) and torch.isfinite(out["d_logits"]).all()
+    net.close()

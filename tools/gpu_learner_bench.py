@@ -68,6 +68,15 @@ def main():
         gb = n * 32 / 1e9          # g twice (norm pass + update), p / mu / nu read and written
         out[name] = {"n": n, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 2}
         del prm, grd, o
+    # value network forward over the rollout (baseline of the loss): 696 -> 1024 -> 1024 -> 1, TF32 tcgen05 GEMMs
+    from track_mjx_b200.policy import ValueNetwork, init_value_params
+
+    rows = B if QUICK else T * B
+    net = ValueNetwork(D, init_value_params(D), max_env=B)
+    xo = x[:rows]
+    ms = timed(lambda: net.apply(xo), reps=5)
+    fl = rows * 2.0 * (D * 1024 + 1024 * 1024 + 1024)
+    out["value_network"] = {"rows": rows, "ms": ms, "algorithmic_TFLOP": fl / 1e12, "TFLOPs": fl / 1e12 / (ms * 1e-3)}
     out["peaks"] = {k: peaks.get(k) for k in ("hbm_gbs", "gpu_name")}
     print(json.dumps(out))
 

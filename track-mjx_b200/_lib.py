@@ -54,6 +54,10 @@ class PolicyDescC(C.Structure):
                 ("n_decoder_layers", C.c_int32), ("decoder_layers", C.c_int32 * 8)]
 
 
+class ValueDescC(C.Structure):
+    _fields_ = [("obs_size", C.c_int32), ("n_hidden_layers", C.c_int32), ("hidden_layers", C.c_int32 * 8)]
+
+
 class DimsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "nq", "nv", "nu", "na", "nbody", "njnt", "ncon", "nefc", "obs_size", "reference_obs_size",
@@ -116,6 +120,10 @@ def load() -> C.CDLL:
     lib.tmjx_policy_param_count.restype = sz
     lib.tmjx_policy_create.argtypes = [C.POINTER(PolicyDescC), fp, sz, i32, i32, C.POINTER(vp)]
     lib.tmjx_policy_destroy.argtypes = [vp]
+    lib.tmjx_value_param_count.argtypes = [C.POINTER(ValueDescC)]
+    lib.tmjx_value_param_count.restype = sz
+    lib.tmjx_value_create.argtypes = [C.POINTER(ValueDescC), fp, sz, i32, i32, C.POINTER(vp)]
+    lib.tmjx_value_apply.argtypes = [vp, vp, vp, i32, vp]
     lib.tmjx_policy_destroy.restype = None
     lib.tmjx_policy_last_error.restype = C.c_char_p
     lib.tmjx_policy_act.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]

@@ -555,6 +555,18 @@ __global__ void gae_kernel(const float* __restrict__ truncation, const float* __
   }
 }
 
+// Value network input / output (brax make_value_network as used at ppo_networks.py:180-185): x = (obs - mean) / std into the
+// K-padded GEMM input; value = column 0 of the last Dense (jnp.squeeze(..., axis=-1))
+__global__ void value_prep_kernel(const float* __restrict__ obs, int obs_size, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                  float* __restrict__ x, int ldx, int n_env) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < obs_size; c += blockDim.x) x[size_t(r) * ldx + c] = (obs[size_t(r) * obs_size + c] - mean[c]) / stdv[c];
+}
+__global__ void value_out_kernel(const float* __restrict__ y, int ldy, float* __restrict__ value, int n_env) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_env) value[r] = y[size_t(r) * ldy];
+}
+
 // ---- PPO loss head (reference losses.py:104-245 after the network applications) ---------------------------------------
 // Three passes over the [T, B] rollout, one warp per transition row in the two wide ones (lanes over the 38 actions and the 60
 // latent dimensions, coalesced row reads, xor-shuffle sums: deterministic):
@@ -1219,6 +1231,86 @@ int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_late
     x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
   }
   action_head_kernel<<<(n_env + 7) / 8, 256, 0, st>>>(x, ldx, d.action_size, eps_action, deterministic, action, raw_action, log_prob, logits, n_env);
+  PCU(cudaGetLastError());
+  return TMJX_OK;
+}
+
+/* Value network, see include/tmjx.h: the TmjxPolicy object with every layer in `enc` (Dense + SiLU, last layer Dense to 1). */
+size_t tmjx_value_param_count(const TmjxValueDesc* d) {
+  if (!d || d->n_hidden_layers < 0 || d->n_hidden_layers > TMJX_POLICY_MAX_LAYERS) return 0;
+  size_t n = 2 * size_t(d->obs_size);
+  int k = d->obs_size;
+  for (int i = 0; i < d->n_hidden_layers; ++i) { n += size_t(k) * d->hidden_layers[i] + d->hidden_layers[i]; k = d->hidden_layers[i]; }
+  return n + size_t(k) + 1;
+}
+int tmjx_value_create(const TmjxValueDesc* d, const float* params, size_t n_params, int device, int max_env, TmjxPolicy** out) {
+  if (!d || !params || !out || max_env <= 0) return pfail(TMJX_E_ARG, "null argument");
+  if (d->obs_size <= 0 || d->n_hidden_layers < 0 || d->n_hidden_layers > TMJX_POLICY_MAX_LAYERS) return pfail(TMJX_E_ARG, "bad value-network shape");
+  if (n_params != tmjx_value_param_count(d)) return pfail(TMJX_E_ARG, "parameter vector has the wrong length");
+  PCU(cudaSetDevice(device));
+  auto* p = new TmjxPolicy();
+  std::unique_ptr<TmjxPolicy, void (*)(TmjxPolicy*)> guard(p, tmjx_policy_destroy);
+  p->d.obs_size = d->obs_size; p->device = device; p->max_env = max_env;
+  const float* cur = params;
+  auto upload = [&](const std::vector<float>& h, float** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(h.size(), 1) * 4);
+    if (e != cudaSuccess) return e;
+    p->owned.push_back(*dst);
+    return cudaMemcpy(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  };
+  {
+    std::vector<float> m(cur, cur + d->obs_size); cur += d->obs_size;
+    std::vector<float> sd(cur, cur + d->obs_size); cur += d->obs_size;
+    PCU(upload(m, &p->norm_mean)); PCU(upload(sd, &p->norm_std));
+  }
+  int k = d->obs_size, widest = 0;
+  for (int i = 0; i <= d->n_hidden_layers; ++i) {
+    const int n = i < d->n_hidden_layers ? d->hidden_layers[i] : 1;
+    if (n <= 0) return pfail(TMJX_E_ARG, "bad hidden layer size");
+    const float* W = cur; cur += size_t(k) * n;
+    const float* b = cur; cur += n;
+    Layer L;
+    L.k = k; L.n = n; L.kpad = pad_to(k, BK); L.npad = n > 256 ? pad_to(n, 256) : pad_to(n, BN);
+    L.act = i < d->n_hidden_layers ? 1 : 0;                  // brax MLP: activation on every layer but the last, no LayerNorm
+    std::vector<float> wt(size_t(L.npad) * L.kpad, 0.f), bb(L.npad, 0.f);
+    for (int r = 0; r < k; ++r) for (int j = 0; j < n; ++j) wt[size_t(j) * L.kpad + r] = W[size_t(r) * n + j];
+    for (int j = 0; j < n; ++j) bb[j] = b[j];
+    PCU(upload(wt, &L.wt)); PCU(upload(bb, &L.bias));
+    p->enc.push_back(L); k = n; widest = std::max(widest, L.npad);
+  }
+  p->ld_buf = widest;
+  p->ld_enc = pad_to(d->obs_size, BK);
+  for (int i = 0; i < 2; ++i) { PCU(cudaMalloc(&p->buf[i], size_t(max_env) * p->ld_buf * 4)); p->owned.push_back(p->buf[i]); PCU(cudaMemset(p->buf[i], 0, size_t(max_env) * p->ld_buf * 4)); }
+  PCU(cudaMalloc(&p->enc_in, size_t(max_env) * p->ld_enc * 4)); p->owned.push_back(p->enc_in);
+  PCU(cudaMemset(p->enc_in, 0, size_t(max_env) * p->ld_enc * 4));   // the K padding columns stay zero
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<128>::kSmem));
+  const float* x = p->enc_in;
+  int ldx = p->ld_enc, pp = 0;
+  for (Layer& L : p->enc) {
+    if (!encode_map(&L.mapW, L.wt, L.npad, L.kpad, L.kpad, L.npad >= 512 ? 256 : 128)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    if (!encode_map(&L.mapX, x, max_env, L.kpad, ldx, 256)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    L.x_bound = x; L.ldx_bound = ldx;
+    x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
+  }
+  *out = guard.release();
+  return TMJX_OK;
+}
+int tmjx_value_apply(const TmjxPolicy* v, const float* obs, float* value, int n_env, void* stream) {
+  if (!v || !obs || !value) return pfail(TMJX_E_ARG, "null argument");
+  if (!v->dec.empty() || v->enc.empty() || v->enc.back().n != 1) return pfail(TMJX_E_ARG, "not a value network");
+  if (n_env <= 0 || n_env > v->max_env) return pfail(TMJX_E_ARG, "n_env exceeds the network's max_env");
+  PCU(cudaSetDevice(v->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  value_prep_kernel<<<n_env, 256, 0, st>>>(obs, v->d.obs_size, v->norm_mean, v->norm_std, v->enc_in, v->ld_enc, n_env);
+  const float* x = v->enc_in;
+  int ldx = v->ld_enc, pp = 0;
+  for (const Layer& L : v->enc) {
+    int rc = run_linear(v, L, x, ldx, v->buf[pp], v->ld_buf, n_env, st);
+    if (rc) return rc;
+    x = v->buf[pp]; ldx = v->ld_buf; pp ^= 1;
+  }
+  value_out_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(x, ldx, value, n_env);
   PCU(cudaGetLastError());
   return TMJX_OK;
 }

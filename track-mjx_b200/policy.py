@@ -146,3 +146,72 @@ class IntentionPolicy:
             self.close()
         except Exception:
             pass
+
+
+def init_value_params(obs_size: int, hidden_layers: Sequence[int] = (1024, 1024), seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random-init parameter tree of the value MLP in flax naming (`hidden_i/kernel` [in, out], `hidden_i/bias`; the last Dense has
+    one output), lecun-uniform like brax's `make_value_network`; identity normaliser."""
+    rng = np.random.default_rng(seed)
+    p = {"norm/mean": np.zeros(obs_size, np.float32), "norm/std": np.ones(obs_size, np.float32)}
+    k = obs_size
+    for i, n in enumerate(list(hidden_layers) + [1]):
+        lim = np.sqrt(3.0 / k)
+        p[f"hidden_{i}/kernel"] = rng.uniform(-lim, lim, (k, n)).astype(np.float32)
+        p[f"hidden_{i}/bias"] = np.zeros(n, np.float32)
+        k = n
+    return p
+
+
+class ValueNetwork:
+    """`value_network.apply(normalizer_params, params.value, obs)` of `ppo_networks.py:180-185` (brax `make_value_network`: normalise,
+    Dense + swish per hidden layer, Dense to 1, squeeze) on the GPU through `tmjx_value_apply`; default hidden sizes are the
+    reference's `value_hidden_layer_sizes=(1024,) * 2` (`ppo_networks.py:165`).  No CPU fallback."""
+
+    def __init__(self, obs_size: int, params: Dict[str, np.ndarray], max_env: int, hidden_layers: Sequence[int] = (1024, 1024), device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("ValueNetwork needs a CUDA device: there is no CPU fallback")
+        self.torch, self.lib, self.max_env = torch, L.load(), int(max_env)
+        self.device = torch.device("cuda", device)
+        self.obs_size = int(obs_size)
+        desc = L.ValueDescC()
+        desc.obs_size, desc.n_hidden_layers = int(obs_size), len(hidden_layers)
+        for i, n in enumerate(hidden_layers):
+            desc.hidden_layers[i] = int(n)
+        parts = [params["norm/mean"], params["norm/std"]]
+        for i in range(len(hidden_layers) + 1):
+            parts += [params[f"hidden_{i}/kernel"], params[f"hidden_{i}/bias"]]
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32).ravel() for a in parts]))
+        if flat.size != self.lib.tmjx_value_param_count(C.byref(desc)):
+            raise ValueError("parameter tree does not match the value-network shape")
+        self._p = C.c_void_p()
+        rc = self.lib.tmjx_value_create(C.byref(desc), flat.ctypes.data_as(C.POINTER(C.c_float)), flat.size, device, self.max_env, C.byref(self._p))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_value_create failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+
+    def apply(self, obs, out=None):
+        """obs: [..., obs_size] fp32 CUDA tensor (any leading dimensions, e.g. [T, B]) -> value [...]."""
+        t = self.torch
+        lead = tuple(obs.shape[:-1])
+        x = obs.reshape(-1, self.obs_size).to(t.float32).contiguous()
+        n = int(x.shape[0])
+        v = t.empty(n, dtype=t.float32, device=self.device) if out is None else out.reshape(-1)
+        st = C.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
+        for i in range(0, n, self.max_env):                          # row chunks of at most max_env (the activation buffers' size)
+            m = min(self.max_env, n - i)
+            rc = self.lib.tmjx_value_apply(self._p, C.c_void_p(x.data_ptr() + 4 * i * self.obs_size), C.c_void_p(v.data_ptr() + 4 * i), m, st)
+            if rc != 0:
+                raise RuntimeError(f"tmjx_value_apply failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+        return v.reshape(lead)
+
+    def close(self):
+        if self._p:
+            self.lib.tmjx_policy_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
