@@ -18,6 +18,11 @@
  * The older two are kept as A/B references (DESIGN.md 3b has the measurements that led from one to the next).  LayerNorm,
  * observation normalisation, the reparameterised latent and the tanh-normal action head are small row-wise kernels around
  * the GEMMs.  All launches are enqueued on the caller's stream; nothing is allocated per call.
+ *
+ * The learner-side kernels of a PPO update live here too: the value-network forward on the same
+ * GEMM (tmjx_value_*), GAE (tmjx_gae, losses.py:39-101), the PPO loss head with its gradient seeds (tmjx_ppo_loss_head,
+ * losses.py:154-245), the observation-normaliser update (tmjx_running_stats_*, masked_running_statistics.py:80-214) and the
+ * optimiser step (tmjx_adam_step, ppo.py:517-520).  They are HBM-bound streaming kernels with fixed-order two-level reductions.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
