@@ -80,3 +80,30 @@ def test_cuda_adam_matches_restatement():
     x, y = torch.zeros(2_600_003, device="cuda"), torch.zeros(2_600_003, device="cuda")
     Adam(x).step(g); Adam(y).step(g)
     assert torch.equal(x, y)
+
+
+def test_shuffle_minibatches_matches_reference_convert_data():
+    """`learner.shuffle_minibatches` on time-major `[T, B, ...]` tensors against a numpy transcription of `convert_data`
+    (ppo.py:305-310: permute axis 0 of `[B, T, ...]`, reshape to `[num_minibatches, -1, T, ...]`): exact, including nested extras."""
+    torch = pytest.importorskip("torch")
+    from track_mjx_b200.learner import shuffle_minibatches
+
+    rng = np.random.default_rng(2)
+    T, B, nm = 5, 24, 4
+    data = {"observation": rng.normal(size=(T, B, 7)).astype(np.float32), "reward": rng.normal(size=(T, B)).astype(np.float32),
+            "extras": {"policy_extras": {"raw_action": rng.normal(size=(T, B, 3)).astype(np.float32)}}}
+    perm = rng.permutation(B)
+
+    def convert_data(x_bt):                                     # the reference's layout and operations
+        x = x_bt[perm]
+        return x.reshape((nm, -1) + x.shape[1:])
+
+    to_t = lambda d: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in d.items()}
+    got = shuffle_minibatches(to_t(data), torch.from_numpy(perm), nm)
+    for leaf, want_src in ((got["observation"], data["observation"]), (got["reward"], data["reward"]),
+                           (got["extras"]["policy_extras"]["raw_action"], data["extras"]["policy_extras"]["raw_action"])):
+        want = convert_data(np.swapaxes(want_src, 0, 1))         # [nm, B / nm, T, ...]
+        assert leaf.shape[:3] == (nm, T, B // nm)
+        assert np.array_equal(np.swapaxes(leaf.numpy(), 1, 2), want)
+    with pytest.raises(ValueError):
+        shuffle_minibatches(to_t(data), torch.from_numpy(perm), 5)

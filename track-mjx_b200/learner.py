@@ -34,6 +34,27 @@ def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambd
     return vs, adv
 
 
+def shuffle_minibatches(data, permutation, num_minibatches: int):
+    """`convert_data` of the reference's `sgd_step` (`track_mjx/agent/mlp_ppo/ppo.py:305-310`) on the time-major layout of the
+    acting loop: every tensor of `data` is `[T, B, ...]` (the reference holds `[B, T, ...]` and permutes / splits axis 0 = B);
+    `permutation` is the `[B]` index vector the reference draws with `jax.random.permutation(key_perm, ...)` (the same one for every
+    leaf).  Returns tensors `[num_minibatches, T, B / num_minibatches, ...]`: minibatch `i` holds environments
+    `permutation[i * B / num_minibatches : (i + 1) * B / num_minibatches]`, ready for `ppo_loss_head`.  Works on any torch device
+    (one gather per leaf; plumbing, not a kernel of this library)."""
+    out = {}
+    for k, x in data.items():
+        if isinstance(x, dict):
+            out[k] = shuffle_minibatches(x, permutation, num_minibatches)
+            continue
+        T, B = x.shape[0], x.shape[1]
+        if B % num_minibatches != 0 or permutation.shape != (B,):
+            raise ValueError(f"{k}: batch of {B} environments cannot be split into {num_minibatches} minibatches with this permutation")
+        y = x.index_select(1, permutation)                                      # jax.random.permutation(key_perm, x) on the env axis
+        y = y.reshape((T, num_minibatches, B // num_minibatches) + tuple(x.shape[2:]))
+        out[k] = y.movedim(1, 0).contiguous()                                   # jnp.reshape(x, (num_minibatches, -1) + x.shape[1:])
+    return out
+
+
 class _PpoHyper(C.Structure):
     _fields_ = [("entropy_cost", C.c_float), ("kl_weight", C.c_float), ("discounting", C.c_float), ("reward_scaling", C.c_float),
                 ("gae_lambda", C.c_float), ("clipping_epsilon", C.c_float), ("normalize_advantage", C.c_int32)]
@@ -165,6 +186,16 @@ class RunningStatistics:
         self._buf = torch.zeros(3 * size + 1, **f)           # row count | sum(x - mean) | batch mean | batch M2
         self._scratch = torch.zeros(int(self.lib.tmjx_running_stats_scratch_floats(size)), **f)
         self.std_min, self.std_max = float(std_min_value), float(std_max_value)
+        self._frozen = None
+
+    def freeze_tail(self, mean, std, summed_variance):
+        """Keep the last `len(mean)` features (the proprioceptive block) at frozen statistics: after every `update` they are written
+        back over the tail of mean / std / summed_variance, as `ppo.py:364-382` does with `frozen_proprioceptive_normalizer_params`."""
+        t = self.torch
+        self._frozen = tuple(t.as_tensor(a, dtype=t.float32, device=self.mean.device).reshape(-1).clone() for a in (mean, std, summed_variance))
+        if not (0 < self._frozen[0].numel() <= self.D) or any(a.numel() != self._frozen[0].numel() for a in self._frozen):
+            raise ValueError("frozen statistics must be three vectors of the same length <= the observation size")
+        return self
 
     def _check(self, rc, what):
         if rc != 0:
@@ -190,4 +221,7 @@ class RunningStatistics:
             dist.all_reduce(self._buf[1 : D + 1])             # SUM over ranks: variance update                (psum at :176-177)
         self._check(lib.tmjx_running_stats_apply(sums, D, self.std_min, self.std_max, ptr(self.count), ptr(self.summed_variance),
                                                  ptr(self.std), ptr(self._scratch), st), "tmjx_running_stats_apply")
+        if self._frozen is not None:
+            k = self._frozen[0].numel()
+            self.mean[-k:].copy_(self._frozen[0]); self.std[-k:].copy_(self._frozen[1]); self.summed_variance[-k:].copy_(self._frozen[2])
         return self
