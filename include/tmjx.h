@@ -144,6 +144,10 @@ typedef struct TmjxOut {
 /* step flags */
 #define TMJX_F_AUTORESET   1u  /* fuse EpisodeWrapper + AutoResetWrapperTracking (wrappers.py:288-310) */
 #define TMJX_F_SNAPSHOT    2u  /* tmjx_forward: also store first_* (wrappers.py:281-286) */
+#define TMJX_F_EPILOGUE_ONLY 4u /* tmjx_step test hook: skip the physics substeps; qpos / qvel / time / xpos / xquat / qfrc_actuator of TmjxState
+                                   are taken as the POST-physics state and only the task layer (single_clip_tracking.py:221-320: frame lookup,
+                                   info updates, rewards, obs, done, metrics) runs on them.  Lets the golden vectors computed by the reference's
+                                   own task code (tests/golden/task_layer.npz) check the CUDA epilogue without the physics in between. */
 
 typedef struct TmjxModel TmjxModel;
 typedef struct TmjxClips TmjxClips;

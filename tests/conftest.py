@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a host without CUDA skips the gpu tests instead of failing on the first one.  On a GPU host a
+    missing libtmjx.so is NOT a skip: the product path must fail loudly there (the tests then error at `_lib.load()`)."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (no GPU on this host); run with -m gpu on the B200 box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def walker():
     from track_mjx_b200.walker import Rodent

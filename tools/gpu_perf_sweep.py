@@ -21,7 +21,7 @@ cl = clipmod.make_synthetic_clips(w.sections, 1)
 args = {k: v for k, v in config.DEFAULT_ENV_ARGS.items() if k != "reset_noise_scale"}
 cfg = config.make_task_config(w, config.RewardConfig(), **args)
 sizes = [int(x) for x in sys.argv[1:]] or [148, 1776, 2072, 4096, 8192]
-tag = f"epb={os.environ.get('TMJX_ENVS_PER_BLOCK', 'auto')} nogen={os.environ.get('TMJX_NO_GEN', '0')}"
+tag = f"epb={os.environ.get('TMJX_ENVS_PER_BLOCK', 'auto')} spill={os.environ.get('TMJX_L2_SPILL', '1')} nogen={os.environ.get('TMJX_NO_GEN', '0')}"
 for nenv in sizes:
     g = Stepper(w.blob, cfg, cl, nenv, 0)
     hb = {k: np.zeros(tuple(v.shape), np.float32 if v.dtype == torch.float32 else np.int32) for k, v in g.buf.items()}

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtmjx.so")
 
 TMJX_F_AUTORESET = 1
 TMJX_F_SNAPSHOT = 2
+TMJX_F_EPILOGUE_ONLY = 4
 
 STATE_FIELDS = (
     # name, per-env shape key, dtype ('f' = float, 'i' = int32)

@@ -44,6 +44,7 @@ struct KArgs {
   const float* action;
   int n_env;
   unsigned flags;
+  float* spill;   // per resident warp: m.spill_floats floats (compact CG layout), else unused
 };
 
 #ifdef TMJX_VARIANT  // device code: compiled once per residency variant, in parallel (see __graft_entry__.build)
@@ -186,6 +187,7 @@ struct Warp {
   float* s;  // this environment's shared-memory slice
   int lane;
   int dep[kNvSlots], rend[kNvSlots];  // depth / row end (sparse L) of the dofs this lane owns
+  float* spill;                       // this warp's global parking slot for the head of the Euler factor (compact layout)
   __device__ __forceinline__ float* at(int off) const { return s + off; }
 };
 
@@ -725,7 +727,7 @@ __device__ void build_m(const Warp& w) {
   const float* cdof = w.at(m.o_cdof);
   float* L1 = w.at(m.o_big);
   float* L2 = w.at(m.o_L2);
-  float* f = L2;  // M-build scratch, dead before L2 is written
+  float* f = w.at(m.o_big + m.a_f);  // M-build scratch, dead before L2 is written
   sum_subtrees<10>(w, crb);
   for (int d = w.lane; d < m.nv; d += 32) {
     float t[6], ci[10], cd[6];
@@ -1337,7 +1339,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   const float* L1 = w.at(m.o_L);
   // the residency variants are solver-specialised: 14 warps = CG only, 10 warps = Newton only (its slice carries a third
   // matrix), 4 warps = either (runtime); dropping the other solver's code shrinks the hot kernel's instruction footprint
-#if TMJX_VARIANT == 14
+#if TMJX_VARIANT >= 14
   constexpr bool newton = false;
 #elif TMJX_VARIANT == 10
   constexpr bool newton = true;
@@ -1550,6 +1552,14 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_he
   }
   __syncwarp();
   if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1, gen::kNMpad); __syncwarp(); } else factor_dual(w);
+  if (m.l2_spill) {
+    // park the head of the Euler factor (it sits where the solver scratch is about to go) in global memory: written once,
+    // read back once per substep by euler(), 2.7 KB per environment that never leaves the L2 cache
+    const float4* src = reinterpret_cast<const float4*>(w.at(m.o_L2));
+    float4* dst = reinterpret_cast<float4*>(w.spill);
+    for (int i = w.lane; i < m.spill_floats / 4; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
   if (m.sync_mask & 4) phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
@@ -1568,6 +1578,13 @@ __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   float qacc[kNvSlots];
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) qacc[q] = fo.qfs[q] + fo.so.qfc[q];
+  if (m.l2_spill) {   // the solver scratch is dead: bring the head of the Euler factor back behind its tail
+    __syncwarp();
+    const float4* src = reinterpret_cast<const float4*>(w.spill);
+    float4* dst = reinterpret_cast<float4*>(w.at(m.o_L2));
+    for (int i = w.lane; i < m.spill_floats / 4; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
   solve_ld(w, w.at(m.o_L2), qacc);
   float* qpos = w.at(m.o_qpos);
   float* qvel = w.at(m.o_qvel);
@@ -1695,7 +1712,8 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
   const DevTask& t = *a.task;
   const TmjxTaskConfig& cfg = t.cfg;
   const int wpb = kWPB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Warp w{m, smem + size_t(warp) * m.smem_floats, lane, {0, 0, 0}, {0, 0, 0}};
+  Warp w{m, smem + size_t(warp) * m.smem_floats, lane, {0, 0, 0}, {0, 0, 0},
+         a.spill + (size_t(blockIdx.x) * kWPB + warp) * size_t(m.spill_floats)};
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) { w.dep[q] = m.depth_me[q * 32 + lane]; w.rend[q] = m.rowend_me[q * 32 + lane]; }
   const int nu = m.nu, nobs = t.obs_size, W = cfg.var_window_size;
@@ -1737,7 +1755,21 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
 
     FwdOut fo;
     float* dbg_dist = (live && a.out.dbg_contact_dist) ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
-    if (kStep) {
+    if (kStep && (a.flags & TMJX_F_EPILOGUE_ONLY)) {
+      // test hook (block-uniform): the given state IS the post-physics state; only the task layer below runs on it
+      for (int i = lane; i < m.nbody * 3; i += 32) w.at(m.o_xpos)[i] = a.st.xpos[size_t(e) * m.nbody * 3 + i];
+      for (int i = lane; i < m.nbody * 4; i += 32) w.at(m.o_xquat)[i] = a.st.xquat[size_t(e) * m.nbody * 4 + i];
+#pragma unroll
+      for (int q = 0; q < kNvSlots; ++q) {
+        const int d = lane + 32 * q;
+        fo.qfa[q] = d < m.nv ? a.st.qfrc_actuator[size_t(e) * m.nv + d] : 0.f;
+        fo.qfs[q] = fo.qas[q] = fo.bias[q] = fo.so.qacc[q] = fo.so.qfc[q] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kRowSlots; ++k) fo.so.force[k] = 0.f;
+      fo.actdot[0] = fo.actdot[1] = 0.f; fo.com[0] = fo.com[1] = fo.com[2] = 0.f;
+      __syncwarp();
+    } else if (kStep) {
       for (int f = 0; f < m.n_frames; ++f) {
         forward(w, fo, f == m.n_frames - 1 ? dbg_dist : nullptr, m.sync_every <= 1 || f % m.sync_every == 0);
         euler(w, fo, time);
@@ -1951,8 +1983,8 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
 }  // namespace
 
 // per-variant entry points (one translation unit per residency variant; the C ABI below dispatches on envs_per_block)
-#if TMJX_VARIANT == 14
-#define TMJX_WPB 14
+#if TMJX_VARIANT >= 14
+#define TMJX_WPB TMJX_VARIANT
 #define TMJX_MINB 1
 #elif TMJX_VARIANT == 10
 #define TMJX_WPB 10
@@ -1986,6 +2018,11 @@ cudaError_t TMJX_CAT(variant_launch_, TMJX_VARIANT)(bool step, const KArgs& a, i
 TMJX_DECL_VARIANT(14)
 #else
 TMJX_STUB_VARIANT(14)
+#endif
+#ifdef TMJX_HAVE_VARIANT_16
+TMJX_DECL_VARIANT(16)
+#else
+TMJX_STUB_VARIANT(16)
 #endif
 #ifdef TMJX_HAVE_VARIANT_10
 TMJX_DECL_VARIANT(10)
@@ -2023,7 +2060,10 @@ struct TmjxModel {
   uint8_t* d_u8 = nullptr;
   float* d_f32 = nullptr;
   int device = 0, sm_count = 0, envs_per_block = 12, max_blocks_per_sm = 1;
-  size_t smem_per_block = 0;
+  int envs_per_block_alt = 0;   // CG: the 16-warp residency variant, taken when it saves a lock-step round for the batch at hand
+  int force_epb = 0;            // TMJX_ENVS_PER_BLOCK
+  size_t smem_per_env = 0;
+  float* d_spill = nullptr;     // [sm_count * max_blocks_per_sm * max envs per block, spill_floats] (compact CG layout)
   TmjxTaskConfig cfg;
 };
 struct TmjxClips {
@@ -2077,13 +2117,21 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   CU(cudaGetDeviceProperties(&prop, device));
   m->sm_count = prop.multiProcessorCount;
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
-  // 7 warps x 2 blocks = 14 resident envs per SM when the per-env slice allows it, else 4 warps x up to 3 blocks
-  // One block per SM with all of its warps in lock-step (phase_sync): 14 resident environments per SM when the per-env
-  // slice allows it (CG), 10 for larger slices (Newton keeps a third sparse matrix), else blocks of 4.
+  m->smem_per_env = per_env;
+  // One block per SM with all of its warps in lock-step (phase_sync).  CG (compact slice, 13.9 KB per environment): 14 warps per
+  // block by default -- 194 KB of shared memory, which leaves the SM a 60 KB L1 for the model tables -- and 16 warps (4 per
+  // scheduler, the register file's limit at 128 registers) whenever that saves a whole lock-step round for the batch at hand
+  // (launch()).  Newton keeps a third sparse matrix: 10 warps.  Blocks of 4 warps are the generic fallback.
   const size_t optin = prop.sharedMemPerBlockOptin;
   const bool is_newton = m->dm.solver == TMJX_SOLVER_NEWTON;
   m->envs_per_block = (!is_newton && per_env * 14 <= optin) ? 14 : ((is_newton && per_env * 10 <= optin) ? 10 : 4);
-  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) { if (atoi(e) == 4) m->envs_per_block = 4; }   // tuning knob
+  m->envs_per_block_alt = (m->envs_per_block == 14 && per_env * 16 <= optin) ? 16 : 0;
+  if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) {   // tuning knob
+    const int v = atoi(e);
+    if (v == 4) { m->envs_per_block = 4; m->envs_per_block_alt = 0; }
+    if (v == 14 && m->envs_per_block == 14) m->envs_per_block_alt = 0;
+    if (v == 16 && m->envs_per_block_alt == 16) { m->envs_per_block = 16; m->envs_per_block_alt = 0; }
+  }
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_DSC4")) { if (atoi(e)) m->dm.use_dsc4 = 0; }                  // tuning knob
@@ -2095,11 +2143,17 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   if (const char* e = std::getenv("TMJX_SYNC_MASK")) m->dm.sync_mask = atoi(e);                          // tuning knob
   m->dm.sync_every = 1;
   if (const char* e = std::getenv("TMJX_SYNC_EVERY")) m->dm.sync_every = std::max(1, atoi(e));           // tuning knob
-  m->smem_per_block = per_env * m->envs_per_block;
-  if (m->smem_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
-  m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (m->smem_per_block + 1024)));
-  const int dyn = int(m->smem_per_block);
-  CU(m->envs_per_block == 14 ? variant_attr_14(dyn) : (m->envs_per_block == 10 ? variant_attr_10(dyn) : variant_attr_4(dyn)));
+  if (per_env * m->envs_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
+  m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (per_env * 4 + 1024)));
+  for (int epb : {m->envs_per_block, m->envs_per_block_alt}) {
+    if (!epb) continue;
+    const int dyn = int(per_env * epb);
+    CU(epb == 16 ? variant_attr_16(dyn) : (epb == 14 ? variant_attr_14(dyn) : (epb == 10 ? variant_attr_10(dyn) : variant_attr_4(dyn))));
+  }
+  {
+    const size_t slots = size_t(m->sm_count) * m->max_blocks_per_sm * std::max(m->envs_per_block, m->envs_per_block_alt);
+    CU(cudaMalloc(&m->d_spill, std::max<size_t>(slots * size_t(m->dm.spill_floats), 4) * 4));
+  }
   *out = guard.release();
   return TMJX_OK;
 }
@@ -2107,7 +2161,7 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
 void tmjx_model_destroy(TmjxModel* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->d_i32); cudaFree(m->d_u16); cudaFree(m->d_u8); cudaFree(m->d_f32); cudaFree(m->d_task);
+  cudaFree(m->d_i32); cudaFree(m->d_u16); cudaFree(m->d_u8); cudaFree(m->d_f32); cudaFree(m->d_task); cudaFree(m->d_spill);
   delete m;
 }
 
@@ -2184,12 +2238,22 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   KArgs a;
   a.m = m->dm; a.task = m->d_task; a.clips = c->d_table; a.n_clips = c->n_clips; a.clip_len = c->clip_len;
   a.st = *s; a.out = *o; a.action = action; a.n_env = n_env; a.flags = flags;
-  const int epb = m->envs_per_block;
+  a.spill = m->d_spill;
+  // residency variant: the block runs ceil(envs of the block / envs per block) lock-step rounds of the same duration whatever the
+  // number of warps, so the wider block is taken exactly when it saves a round (4096 envs on 148 SMs: 28 per SM = 2 rounds either
+  // way -> 14 warps and the larger L1; 16384: 111 per SM = 8 rounds of 14 or 7 of 16)
+  int epb = m->envs_per_block;
+  if (m->envs_per_block_alt) {
+    const int per_sm = (n_env + m->sm_count - 1) / m->sm_count, alt = m->envs_per_block_alt;
+    if ((per_sm + alt - 1) / alt < (per_sm + epb - 1) / epb) epb = alt;
+  }
   const int need = (n_env + epb - 1) / epb;
   const int grid = std::min(need, m->sm_count * m->max_blocks_per_sm);
+  const size_t smem = m->smem_per_env * epb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(epb == 14 ? variant_launch_14(kStep, a, grid, m->smem_per_block, st)
-               : (epb == 10 ? variant_launch_10(kStep, a, grid, m->smem_per_block, st) : variant_launch_4(kStep, a, grid, m->smem_per_block, st)));
+  CU(epb == 16 ? variant_launch_16(kStep, a, grid, smem, st)
+               : (epb == 14 ? variant_launch_14(kStep, a, grid, smem, st)
+                            : (epb == 10 ? variant_launch_10(kStep, a, grid, smem, st) : variant_launch_4(kStep, a, grid, smem, st))));
   return TMJX_OK;
 }
 

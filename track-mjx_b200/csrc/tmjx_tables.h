@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -128,6 +129,11 @@ struct DevModel {
   // re-used every iteration for H = M + J^T D J and M*search) and factors a copy: o_L = o_big + nMpad, which is also
   // where H is assembled and factored.  f (M-build scratch) aliases the o_L2 block.
   int nMpad, o_L, o_L2;
+  // Compact CG layout (l2_spill = 1): o_cin sits directly behind the factor of M (o_L2 = o_cin = o_L + nMpad), so the Euler
+  // factor is BUILT over the dead composite-inertia block + a tail block; its first spill_floats floats (the part the solver
+  // scratch needs back) are parked in a per-warp global (L2-cache resident) buffer between the factorisation and forward.euler.
+  // a_f: M-build scratch (relative to o_big).
+  int l2_spill, spill_floats, a_f;
   // solver-phase scratch inside o_cin
   int c_sx, c_sy, c_sD, c_sV, c_sW, c_sWb, c_off, c_t1, c_lf, c_sP, c_end;
 };
@@ -562,7 +568,8 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
   auto take = [&](int n) { int r = o; o += pad4(n); return r; };
   m.o_qpos = take(m.nq); m.o_qvel = take(nv); m.o_act = take(std::max(m.na, 1)); m.o_ctrl = take(nu); m.o_warm = take(nv);
   m.o_xpos = take(nbody * 3); m.o_xquat = take(nbody * 4); m.o_cdof = take(nv * 6);
-  m.o_cin = o;
+  m.nMpad = pad4(m.nM);
+  int cin_size = 0;
   {
     int c = 0;
     auto tk = [&](int n) { int r = c; c += pad4(n); return r; };
@@ -570,19 +577,43 @@ inline void build_tables(const Blob& b, const TmjxTaskConfig& cfg, HostTables& t
     m.c_off = tk(m.ncon * 3); m.c_t1 = tk(m.ncon * 3); m.c_lf = tk(m.nlimit);
     m.c_sP = tk(64);
     m.c_end = c;
-    o += std::max(pad4(nbody * 10), c);
+    cin_size = std::max(pad4(nbody * 10), c);
   }
-  m.o_big = o;
-  m.nMpad = pad4(m.nM);
-  {
+  if (pad4(nv * 6) > m.nMpad) throw std::runtime_error("M-build scratch does not fit");
+  m.l2_spill = (m.solver == TMJX_SOLVER_CG) ? 1 : 0;
+  if (const char* e = std::getenv("TMJX_L2_SPILL")) m.l2_spill = (atoi(e) != 0 && m.solver == TMJX_SOLVER_CG) ? 1 : 0;   // tuning knob
+  m.spill_floats = 0;
+  if (m.l2_spill) {
+    // [ L = factor of M (nMpad) | cin (cin_size) | tail ]   with the Euler factor L2 over cin + tail.
+    // Phase A transients live in the L block and the tail (both dead until build_m writes the matrices):
+    //   kinematics -> com_pos : anchor, axis (aliased later by cvel), xipos          (L block)
+    //   com_vel_rne           : cvel, cacc (L block), cdof_dot (tail)
+    //   passive_actuation     : force (L block);   build_m: f (tail, after cdof_dot died)
+    m.o_big = o;
+    m.o_L = m.o_big; m.o_cin = m.o_big + m.nMpad; m.o_L2 = m.o_cin;
+    const int tail = std::max(std::max(m.nMpad - cin_size, 0), pad4(nv * 6));
+    const int o_tail = m.nMpad + cin_size;       // relative to o_big
+    int a = 0;
+    auto tk = [&](int n) { int r = a; a += pad4(n); return r; };
+    m.a_cvel = tk(nbody * 6); m.a_anchor = m.a_cvel; m.a_axis = m.a_anchor + pad4(njnt * 3);
+    if (2 * pad4(njnt * 3) > pad4(nbody * 6)) a = m.a_anchor + 2 * pad4(njnt * 3);
+    m.a_cacc = tk(nbody * 6); m.a_xipos = tk(nbody * 3); m.a_force = tk(nu);
+    if (a > m.nMpad) throw std::runtime_error("smooth-dynamics transients do not fit the compact layout (unsupported)");
+    m.a_cdofdot = o_tail; m.a_f = o_tail;
+    m.spill_floats = cin_size;
+    o += m.nMpad + cin_size + tail;
+  } else {
+    m.o_cin = o;
+    o += cin_size;
+    m.o_big = o;
     int a = 0;
     auto tk = [&](int n) { int r = a; a += pad4(n); return r; };
     m.a_xipos = tk(nbody * 3); m.a_anchor = tk(njnt * 3); m.a_axis = tk(njnt * 3); m.a_cvel = tk(nbody * 6);
     m.a_cdofdot = tk(nv * 6); m.a_cacc = tk(nbody * 6); m.a_force = tk(nu);
-    if (pad4(nv * 6) > m.nMpad) throw std::runtime_error("M-build scratch does not fit");
     const int nmat = m.solver == TMJX_SOLVER_NEWTON ? 3 : 2;
     m.o_L = m.o_big + (nmat - 2) * m.nMpad;
     m.o_L2 = m.o_L + m.nMpad;
+    m.a_f = m.o_L2 - m.o_big;     // M-build scratch aliases the (not yet written) Euler-factor block
     o += std::max(a, nmat * m.nMpad);
   }
   if (m.solver == TMJX_SOLVER_NEWTON)
