@@ -13,7 +13,7 @@ import os
 from .config import TaskConfigC, TMJX_N_METRICS
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtmjx.so")
+LIB_PATH = os.environ.get("TMJX_LIB_PATH") or os.path.join(_HERE, "csrc", "libtmjx.so")   # TMJX_LIB_PATH: development builds (tools/gpu_phase_timing.py)
 
 TMJX_F_AUTORESET = 1
 TMJX_F_SNAPSHOT = 2

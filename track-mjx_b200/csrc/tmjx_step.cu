@@ -52,6 +52,23 @@ namespace {      // internal linkage: every variant translation unit carries its
 #define FULLMASK 0xffffffffu
 constexpr float kMinVal = 1e-15f;
 
+// Phase timers (development builds only, -DTMJX_PHASE_TIMING; tools/gpu_phase_timing.py): warp 0 of block 0 accumulates the
+// clock64() cycles it spends in each phase of a substep -- the critical path of ONE environment, which is what bounds the
+// lock-step round time.
+#ifdef TMJX_PHASE_TIMING
+__device__ unsigned long long g_pt[64];
+struct PhaseTimer {
+  long long t; bool on;
+  __device__ __forceinline__ PhaseTimer() : t(0), on(blockIdx.x == 0 && threadIdx.x == 0) { if (on) t = clock64(); }
+  __device__ __forceinline__ void lap(int i) { if (on) { const long long n = clock64(); g_pt[i] += (unsigned long long)(n - t); t = n; } }
+};
+#define PT_DECL PhaseTimer pt_
+#define PT_LAP(i) pt_.lap(i)
+#else
+#define PT_DECL
+#define PT_LAP(i)
+#endif
+
 // ---------------------------------------------------------------------------------------------- device math
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
@@ -1348,6 +1365,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
 #endif
   float warm[kNvSlots];
   vget(w, w.at(m.o_warm), warm);
+  PT_DECL;
 
   // ---- warm-start choice: cost(qacc_warmstart) vs cost(qacc_smooth)
   float Jw[kRowSlots], Js[kRowSlots];
@@ -1368,6 +1386,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   cw = 0.5f * wsum(cw) + 0.5f * wsum(gw);
   cs = 0.5f * wsum(cs);  // gauss(qacc_smooth) == 0 exactly
   const bool use_warm = cw < cs;
+  PT_LAP(16);
 
   float qacc[kNvSlots], Ma[kNvSlots], Jaref[kRowSlots];
 #pragma unroll
@@ -1413,6 +1432,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q]; mv[q] = -grad[q]; }
   }
+  PT_LAP(17);
   const float scale = m.meaninertia_scale;
   // The iteration count is block-uniform (phase barriers inside): an environment whose solver has terminated
   // (solver.py's while_loop cond) is masked for the remaining rounds instead of breaking out.
@@ -1442,7 +1462,9 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
         mul_m_raw(w, sx, mv);
       }
     }
+    PT_LAP(18);
     apply_J(w, r, sx, jv);
+    PT_LAP(19);
     float qg[3];
     {
       float a = 0.f, b = 0.f, c = 0.f;
@@ -1487,6 +1509,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
       if (swap_hi_mid) hi = mid;
       swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
     }
+    PT_LAP(20);
     const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
     if (improved) {
@@ -1502,8 +1525,11 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     float pg[kNvSlots], pMg[kNvSlots];
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { pg[q] = grad[q]; pMg[q] = Mgrad[q]; }
+    PT_LAP(21);
     update_constraint(true);
+    PT_LAP(22);
     update_gradient();
+    PT_LAP(23);
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { num += grad[q] * (Mgrad[q] - pMg[q]); den += pg[q] * pMg[q]; }
@@ -1512,6 +1538,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
     if (newton) beta = 0.f;  // search = -H^-1 grad
 #pragma unroll
     for (int q = 0; q < kNvSlots; ++q) { search[q] = -Mgrad[q] + beta * search[q]; mv[q] = -grad[q] + beta * mv[q]; }
+    PT_LAP(24);
     }
   }
 #pragma unroll
@@ -1528,16 +1555,23 @@ struct FwdOut {
 
 __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_here = true) {
   const DevModel& m = w.m;
+  PT_DECL;
   if (m.sync_level >= 0 && sync_here) phase_sync();
+  PT_LAP(0);
   kinematics(w);
+  PT_LAP(1);
   if (m.sync_level > 1) phase_sync();
   com_pos(w, fo.com);
+  PT_LAP(2);
   if (m.sync_level > 1) phase_sync();
   com_vel_rne(w, fo.bias);
+  PT_LAP(3);
   if (m.sync_mask & 1) phase_sync();
   passive_actuation(w, fo.bias, fo.qfa, fo.qfs, fo.actdot);
   __syncwarp();
+  PT_LAP(4);
   build_m(w);
+  PT_LAP(5);
   if (m.sync_mask & 2) phase_sync();
   float Maw[kNvSlots];   // M qacc_warmstart, while o_big still holds the raw inertia
   if (m.use_gen) {
@@ -1551,7 +1585,9 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_he
     mul_m_raw(w, w.at(m.o_warm), Maw);
   }
   __syncwarp();
+  PT_LAP(6);
   if (m.use_gen) { gen::factor_dual(w.at(m.o_L), w.lane, m.sync_level > 1, gen::kNMpad); __syncwarp(); } else factor_dual(w);
+  PT_LAP(7);
   if (m.l2_spill) {
     // park the head of the Euler factor (it sits where the solver scratch is about to go) in global memory: written once,
     // read back once per substep by euler(), 2.7 KB per environment that never leaves the L2 cache
@@ -1560,14 +1596,18 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_he
     for (int i = w.lane; i < m.spill_floats / 4; i += 32) dst[i] = src[i];
     __syncwarp();
   }
+  PT_LAP(8);
   if (m.sync_mask & 4) phase_sync();
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) fo.qas[q] = fo.qfs[q];
   solve_ld(w, w.at(m.o_L), fo.qas);
+  PT_LAP(9);
   Rows r;
   make_constraint(w, fo.com, r, dbg_dist);
+  PT_LAP(10);
   if (m.sync_mask & 8) phase_sync();
   solve_cg(w, r, fo.qfs, fo.qas, Maw, fo.so);
+  PT_LAP(11);
   vput(w, w.at(m.o_warm), fo.so.qacc);
   __syncwarp();
 }
@@ -1575,6 +1615,7 @@ __device__ void forward(const Warp& w, FwdOut& fo, float* dbg_dist, bool sync_he
 // forward.euler + _advance
 __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   const DevModel& m = w.m;
+  PT_DECL;
   float qacc[kNvSlots];
 #pragma unroll
   for (int q = 0; q < kNvSlots; ++q) qacc[q] = fo.qfs[q] + fo.so.qfc[q];
@@ -1621,6 +1662,7 @@ __device__ void euler(const Warp& w, const FwdOut& fo, float& time) {
   }
   time = __fadd_rn(time, m.dt);
   __syncwarp();
+  PT_LAP(12);
 }
 
 // ---------------------------------------------------------------------------------------------- task layer
@@ -1753,6 +1795,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
     if (kStep && (a.flags & TMJX_F_AUTORESET)) prev_done = a.out.done[e];
     __syncwarp();
 
+    PT_DECL;
     FwdOut fo;
     float* dbg_dist = (live && a.out.dbg_contact_dist) ? a.out.dbg_contact_dist + size_t(e) * m.ncon : nullptr;
     if (kStep && (a.flags & TMJX_F_EPILOGUE_ONLY)) {
@@ -1778,6 +1821,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
       forward(w, fo, dbg_dist);
     }
 
+    PT_LAP(13);
     if (live) {
     // ---- NaN scan over the state this build materialises (stand-in for ravel_pytree(data), :290-293)
     bool bad = isnan(time);
@@ -1977,6 +2021,7 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
     }
     }  // live
     __syncwarp();
+    PT_LAP(14);
   }
 }
 
@@ -1995,14 +2040,25 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
 #endif
 #define TMJX_CAT2(a, b) a##b
 #define TMJX_CAT(a, b) TMJX_CAT2(a, b)
+#ifdef TMJX_PHASE_TIMING
+extern "C" int tmjx_debug_phase_times(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, g_pt, sizeof(g_pt)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[64] = {0}; if (cudaMemcpyToSymbol(g_pt, z, sizeof(z)) != cudaSuccess) return -1; }
+  return 0;
+}
+#endif
 cudaError_t TMJX_CAT(variant_attr_, TMJX_VARIANT)(int dyn) {
   cudaError_t e = cudaFuncSetAttribute(tmjx_env_kernel<true, TMJX_WPB, TMJX_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tmjx_env_kernel<false, TMJX_WPB, TMJX_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
 }
 cudaError_t TMJX_CAT(variant_launch_, TMJX_VARIANT)(bool step, const KArgs& a, int grid, size_t smem, cudaStream_t st) {
-  if (step) tmjx_env_kernel<true, TMJX_WPB, TMJX_MINB><<<grid, TMJX_WPB * 32, smem, st>>>(a);
-  else tmjx_env_kernel<false, TMJX_WPB, TMJX_MINB><<<grid, TMJX_WPB * 32, smem, st>>>(a);
+  // TMJX_DEBUG_WARPS = k (timing experiment only, results are INVALID): launch k of the block's warps; the environments of the
+  // missing warps are skipped.  Gives the round time as a function of the number of resident warps (tools/gpu_warp_scaling.py).
+  static const int dbg_warps = [] { const char* e = std::getenv("TMJX_DEBUG_WARPS"); return e ? atoi(e) : 0; }();
+  const int threads = (dbg_warps > 0 && dbg_warps < TMJX_WPB ? dbg_warps : TMJX_WPB) * 32;
+  if (step) tmjx_env_kernel<true, TMJX_WPB, TMJX_MINB><<<grid, threads, smem, st>>>(a);
+  else tmjx_env_kernel<false, TMJX_WPB, TMJX_MINB><<<grid, threads, smem, st>>>(a);
   return cudaGetLastError();
 }
 }  // namespace tmjx
@@ -2119,18 +2175,21 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   const size_t per_env = size_t(m->dm.smem_floats) * 4;
   m->smem_per_env = per_env;
   // One block per SM with all of its warps in lock-step (phase_sync).  CG (compact slice, 13.9 KB per environment): 14 warps per
-  // block by default -- 194 KB of shared memory, which leaves the SM a 60 KB L1 for the model tables -- and 16 warps (4 per
-  // scheduler, the register file's limit at 128 registers) whenever that saves a whole lock-step round for the batch at hand
-  // (launch()).  Newton keeps a third sparse matrix: 10 warps.  Blocks of 4 warps are the generic fallback.
+  // block -- 194 KB of shared memory, which leaves the SM a 60 KB L1 for the model tables; a 16-warp variant (4 per scheduler, the
+  // register file's limit at 128 registers) exists behind a knob.  Newton keeps a third sparse matrix: 10 warps.  Blocks of 4
+  // warps are the generic fallback.
   const size_t optin = prop.sharedMemPerBlockOptin;
   const bool is_newton = m->dm.solver == TMJX_SOLVER_NEWTON;
   m->envs_per_block = (!is_newton && per_env * 14 <= optin) ? 14 : ((is_newton && per_env * 10 <= optin) ? 10 : 4);
-  m->envs_per_block_alt = (m->envs_per_block == 14 && per_env * 16 <= optin) ? 16 : 0;
+  // measured (profiles/r2b_warp_scaling.txt): a round of 16 warps takes 1.14 x a round of 14, so the wide block only pays when it saves
+  // more than one round in eight; it is opt-in (TMJX_WIDE_BLOCKS=1: launch() then takes it when it saves a round, e.g. 16384 envs)
+  m->envs_per_block_alt = 0;
+  if (const char* e = std::getenv("TMJX_WIDE_BLOCKS")) { if (atoi(e) && m->envs_per_block == 14 && per_env * 16 <= optin) m->envs_per_block_alt = 16; }
   if (const char* e = std::getenv("TMJX_ENVS_PER_BLOCK")) {   // tuning knob
     const int v = atoi(e);
     if (v == 4) { m->envs_per_block = 4; m->envs_per_block_alt = 0; }
     if (v == 14 && m->envs_per_block == 14) m->envs_per_block_alt = 0;
-    if (v == 16 && m->envs_per_block_alt == 16) { m->envs_per_block = 16; m->envs_per_block_alt = 0; }
+    if (v == 16 && m->envs_per_block == 14 && per_env * 16 <= optin) { m->envs_per_block = 16; m->envs_per_block_alt = 0; }
   }
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
