@@ -355,6 +355,114 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_ppo(args, rank, world, local_rank):
+    """BASELINE configs[3]: rodent-mc-intention PPO training, 65536 envs sharded over the GPUs of the job, NCCL gradient all-reduce.
+    One "step" = one training step of the reference (ppo.py:320-395): unroll_length env steps on every env with the intention
+    network in the loop, the normaliser update and num_updates_per_batch x num_minibatches minibatch updates (forward, loss head,
+    backward, all-reduce, Adam).  value = env-steps/s INCLUDING the update; strong scaling (the 65536 envs are split over the ranks)."""
+    import torch
+
+    from track_mjx_b200.env import MultiClipTracking, wrap
+    from track_mjx_b200.policy import IntentionNetworkConfig
+    from track_mjx_b200.ppo import PPO, PPOConfig
+    from track_mjx_b200.sharding import Shard, max_over_ranks
+
+    total_envs = args.ppo_envs
+    if total_envs % (world * 16):
+        raise SystemExit("--ppo-envs must be divisible by 16 x the number of GPUs")
+    B = total_envs // world
+    shard = Shard(rank, world, total_envs)
+    dist = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    walker, clips, config = build_env_pieces(args.ppo_clips)
+    env = wrap(MultiClipTracking(clips, walker, config.RewardConfig(), num_envs=B, device=local_rank, **dict(config.DEFAULT_ENV_ARGS)))
+    pcfg = IntentionNetworkConfig(obs_size=env.observation_size, reference_obs_size=env.stepper.dims["reference_obs_size"], action_size=env.action_size)
+    ppo = PPO(env, pcfg, PPOConfig())
+    ppo.reset(shard.seed(1000))
+    K, W = args.steps, max(1, min(args.warmup, 3))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(W):
+        ppo.training_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ppo.timing = True
+    phases = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        losses = ppo.training_step()
+        torch.cuda.synchronize()
+        for k, v in ppo.phase_ms().items():
+            phases[k] = phases.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    max_ms = max_over_ranks(dev_ms, dev, shard)
+    ppo.timing = False
+    # the same steps with the gradient all-reduce switched off: the difference is what the collective costs when it is NOT hidden
+    exposed_ms = None
+    if world > 1:
+        ppo.all_reduce = False
+        barrier()
+        e0.record()
+        for _ in range(K):
+            ppo.training_step()
+        e1.record()
+        barrier()
+        exposed_ms = (dev_ms - e0.elapsed_time(e1)) / K
+        ppo.all_reduce = True
+    env_steps = B * ppo.T * world
+    value = env_steps * K / (max_ms * 1e-3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    c = ppo.cfg
+    n_mb = c.num_updates_per_batch * c.num_minibatches
+    rows = ppo.T * ppo.Bm
+    flops_mb = rows * 3 * (5.48e6 + 3.1e6)          # forward + dgrad + wgrad of the policy (5.48 MFLOP / row) and the value net (3.1)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 env / tf32 tensor-core GEMMs with fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"rodent-mc-intention PPO training, {total_envs} envs sharded over {world} B200, NCCL gradient all-reduce (BASELINE configs[3])",
+                   "global_envs": total_envs, "envs_per_gpu": B, "n_clips": args.ppo_clips, "unroll_length": ppo.T, "num_minibatches": c.num_minibatches,
+                   "num_updates_per_batch": c.num_updates_per_batch, "minibatch_rows_per_gpu": rows,
+                   "networks": "intention encoder 470-1024-512x4-(60|60), decoder 286-512x3-256x2-76, critic 696-512x5-256-1 (rodent-full-clips.yaml:50-57)",
+                   "parallelism": f"data-parallel x{world}: env shard + minibatch shard per GPU, SUM all-reduce of the flat gradient per minibatch",
+                   "l2": "working set (rollout 3.8 GB at 65536 envs) far exceeds L2; no flush"},
+        "clocks": clocks,
+        "phases_ms_per_step": {k: v / K for k, v in phases.items()},
+        "learner": {"minibatch_updates_per_step": n_mb, "ms_per_minibatch": phases.get("sgd", 0.0) / K / n_mb,
+                    "gemm_tflops_tf32": flops_mb * n_mb / (phases.get("sgd", 1e-9) / K * 1e-3) / 1e12,
+                    "gradient_bytes": int(ppo.trainer.n_params) * 4,
+                    "allreduce_exposed_ms_per_step": exposed_ms,
+                    "allreduce_share_of_step": None if exposed_ms is None else exposed_ms / (max_ms / K)},
+        "gpu_launches": None, "wall_s_timed_region": wall, "losses_last_minibatch": [float(x) for x in losses.cpu()],
+    }
+    emit(out)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def cpu_baseline_leg(walker, clips, config):
     """The oracle port on the host cores of this box, bounded to ~10-20 s."""
     import numpy as np
@@ -407,8 +515,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="tracking", choices=sorted(WORKLOADS),
-                    help="tracking = BASELINE configs[1] (the bench line); intention = configs[2]; contact = configs[4]")
+    ap.add_argument("--workload", default="tracking", choices=sorted(WORKLOADS) + ["ppo"],
+                    help="tracking = BASELINE configs[1] (the bench line); intention = configs[2]; ppo = configs[3]; contact = configs[4]")
+    ap.add_argument("--ppo-envs", type=int, default=65536, help="global number of envs of the ppo workload (split over the GPUs)")
+    ap.add_argument("--ppo-clips", type=int, default=842)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -416,6 +526,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "ppo":
+        run_ppo(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -299,6 +299,40 @@ size_t tmjx_adam_scratch_floats(void);
 int tmjx_adam_step(float* params, const float* grads, float* mu, float* nu, size_t n, float learning_rate, float b1, float b2, float eps,
                    float max_grad_norm, float grad_scale, int count, float* grad_norm_out, float* scratch, void* stream);
 
+/* Refresh an acting policy (tmjx_policy_create) or value network (tmjx_value_create) from a flat DEVICE parameter vector in the layout
+ * of its create call (normaliser mean, std first): the hand-off from the learner to the actor after every optimiser / normaliser
+ * update.  The reference has no such step because its policy closure reads `training_state.params` directly (ppo.py:326-328). */
+int tmjx_policy_set_params(TmjxPolicy* p, const float* params_device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward pass of the intention network and the value network: what `jax.value_and_grad(compute_ppo_loss)` differentiates through
+ * the networks for one minibatch.  Replaces
+ *   gradient_update_fn = gradients.gradient_update_fn(loss_fn, optimizer, pmap_axis_name, has_aux=True)   reference ppo.py:621-623
+ *   (the value_and_grad half; the optimiser half is tmjx_adam_step, the pmean is the caller's NCCL all-reduce of `grads`)
+ * The trainer owns ONE flat fp32 DEVICE parameter buffer = [policy vector | value vector], each in the layout of tmjx_policy_create /
+ * tmjx_value_create (normaliser mean, std at the head of each; they receive zero gradient), and a gradient buffer of the same
+ * layout.  One minibatch:
+ *   tmjx_trainer_policy_forward   obs [rows, obs], eps_latent [rows, L] -> logits [rows, 2 A], latent mean / logvar [rows, L]
+ *   tmjx_trainer_value_forward    obs [rows, obs] -> value [rows]
+ *   tmjx_ppo_loss_head            -> d_logits, d_latent_mean, d_latent_logvar, d_baseline
+ *   tmjx_trainer_value_backward / tmjx_trainer_policy_backward   -> grads (each parameter written once per call)
+ *   all-reduce(grads); tmjx_adam_step(params, grads, ...); tmjx_trainer_sync (parameters -> GEMM operand layouts)
+ * All array arguments are DEVICE pointers, row-major; rows <= max_rows.  Dense layers, dgrad and wgrad run on the tcgen05 TF32 GEMM. */
+typedef struct TmjxTrainer TmjxTrainer;
+int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const float* policy_params /* host */, const float* value_params /* host */,
+                        int device, int max_rows, TmjxTrainer** out);
+void tmjx_trainer_destroy(TmjxTrainer* t);
+size_t tmjx_trainer_param_count(const TmjxTrainer* t);          /* policy vector + value vector */
+size_t tmjx_trainer_policy_param_count(const TmjxTrainer* t);   /* offset of the value vector */
+int tmjx_trainer_buffers(TmjxTrainer* t, float** params, float** grads);
+int tmjx_trainer_sync(TmjxTrainer* t, void* stream);
+int tmjx_trainer_policy_forward(TmjxTrainer* t, const float* obs, const float* eps_latent, int rows, float* logits, float* latent_mean,
+                                float* latent_logvar, void* stream);
+int tmjx_trainer_policy_backward(TmjxTrainer* t, const float* d_logits, const float* d_latent_mean, const float* d_latent_logvar, int rows,
+                                 void* stream);
+int tmjx_trainer_value_forward(TmjxTrainer* t, const float* obs, int rows, float* value, void* stream);
+int tmjx_trainer_value_backward(TmjxTrainer* t, const float* d_value, int rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

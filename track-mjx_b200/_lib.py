@@ -142,6 +142,20 @@ def load() -> C.CDLL:
     lib.tmjx_adam_scratch_floats.restype = sz
     lib.tmjx_adam_step.argtypes = [vp, vp, vp, vp, sz] + [C.c_float] * 6 + [i32, vp, vp, vp]
     lib.tmjx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, vp]
+    lib.tmjx_policy_set_params.argtypes = [vp, vp, vp]
+    lib.tmjx_trainer_create.argtypes = [C.POINTER(PolicyDescC), C.POINTER(ValueDescC), fp, fp, i32, i32, C.POINTER(vp)]
+    lib.tmjx_trainer_destroy.argtypes = [vp]
+    lib.tmjx_trainer_destroy.restype = None
+    lib.tmjx_trainer_param_count.argtypes = [vp]
+    lib.tmjx_trainer_param_count.restype = sz
+    lib.tmjx_trainer_policy_param_count.argtypes = [vp]
+    lib.tmjx_trainer_policy_param_count.restype = sz
+    lib.tmjx_trainer_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.tmjx_trainer_sync.argtypes = [vp, vp]
+    lib.tmjx_trainer_policy_forward.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.tmjx_trainer_policy_backward.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.tmjx_trainer_value_forward.argtypes = [vp, vp, i32, vp, vp]
+    lib.tmjx_trainer_value_backward.argtypes = [vp, vp, i32, vp]
     if lib.tmjx_abi_version() != 1:
         raise ImportError("libtmjx.so ABI version mismatch")
     _lib = lib

@@ -993,6 +993,10 @@ __global__ void stats_apply_kernel(const float* __restrict__ var, int D, float s
 struct Layer {
   int k = 0, n = 0, kpad = 0, npad = 0, act = 0, ln = 0;
   float *wt = nullptr, *bias = nullptr, *ln_scale = nullptr, *ln_bias = nullptr;
+  // where the layer's parameters sit in the flat parameter vector (floats from its start): kernel [k, n1] + bias [n1], for the
+  // fused (mean | logvar) head a second kernel [k, n - n1] + bias; LayerNorm scale / bias.  Used by tmjx_*_set_params and the trainer.
+  size_t off_w = 0, off_b = 0, off_w2 = 0, off_b2 = 0, off_lns = 0, off_lnb = 0;
+  int n1 = 0;
   CUtensorMap mapW;                 // [npad rows, kpad] fp32, box 32 x BN, 128-byte swizzle
   CUtensorMap mapX;                 // the layer's input buffer inside tmjx_policy_act ([max_env rows, kpad], box 32 x 256)
   const float* x_bound = nullptr;   // the buffer mapX was encoded for
@@ -1102,6 +1106,8 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
     cudaError_t e = dense(k, n, W, b, L);
     if (e != cudaSuccess) return e;
     L.act = 1; L.ln = 1;
+    L.off_w = size_t(W - params); L.off_b = size_t(b - params); L.n1 = n;
+    L.off_lns = size_t(cur - params); L.off_lnb = L.off_lns + size_t(n);
     std::vector<float> g(cur, cur + n); cur += n;
     std::vector<float> be(cur, cur + n); cur += n;
     g.resize(L.npad, 0.f); be.resize(L.npad, 0.f);
@@ -1120,7 +1126,9 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
     std::vector<float> W(size_t(k) * 2 * lat), b(2 * lat);
     for (int i = 0; i < k; ++i) for (int j = 0; j < lat; ++j) { W[size_t(i) * 2 * lat + j] = Wm[size_t(i) * lat + j]; W[size_t(i) * 2 * lat + lat + j] = Wl[size_t(i) * lat + j]; }
     for (int j = 0; j < lat; ++j) { b[j] = bm[j]; b[lat + j] = bl[j]; }
-    Layer L; PCU(dense(k, 2 * lat, W.data(), b.data(), L)); p->enc.push_back(L); widest = std::max(widest, L.npad);
+    Layer L; PCU(dense(k, 2 * lat, W.data(), b.data(), L));
+    L.off_w = size_t(Wm - params); L.off_b = size_t(bm - params); L.off_w2 = size_t(Wl - params); L.off_b2 = size_t(bl - params); L.n1 = lat;
+    p->enc.push_back(L); widest = std::max(widest, L.npad);
   }
   k = d->latent_size + d->obs_size - d->reference_obs_size;
   for (int i = 0; i < d->n_decoder_layers; ++i) {
@@ -1129,7 +1137,8 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   {
     const int n = 2 * d->action_size;
     const float* W = cur; cur += size_t(k) * n; const float* b = cur; cur += n;
-    Layer L; PCU(dense(k, n, W, b, L)); p->dec.push_back(L); widest = std::max(widest, L.npad);
+    Layer L; PCU(dense(k, n, W, b, L)); L.off_w = size_t(W - params); L.off_b = size_t(b - params); L.n1 = n;
+    p->dec.push_back(L); widest = std::max(widest, L.npad);
   }
   p->ld_buf = widest;
   p->ld_enc = pad_to(d->reference_obs_size, BK);
@@ -1277,6 +1286,7 @@ int tmjx_value_create(const TmjxValueDesc* d, const float* params, size_t n_para
     Layer L;
     L.k = k; L.n = n; L.kpad = pad_to(k, BK); L.npad = n > 256 ? pad_to(n, 256) : pad_to(n, BN);
     L.act = i < d->n_hidden_layers ? 1 : 0;                  // brax MLP: activation on every layer but the last, no LayerNorm
+    L.off_w = size_t(W - params); L.off_b = size_t(b - params); L.n1 = n;
     std::vector<float> wt(size_t(L.npad) * L.kpad, 0.f), bb(L.npad, 0.f);
     for (int r = 0; r < k; ++r) for (int j = 0; j < n; ++j) wt[size_t(j) * L.kpad + r] = W[size_t(r) * n + j];
     for (int j = 0; j < n; ++j) bb[j] = b[j];
@@ -1427,3 +1437,5 @@ int tmjx_policy_launches_per_act(const TmjxPolicy* p) {
 }
 
 }  // extern "C"
+
+#include "tmjx_train.cuh"

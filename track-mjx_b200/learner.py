@@ -1,6 +1,6 @@
 """Learner-side pieces that sit next to the acting loop: GAE, the observation-normaliser update and the
 PPO loss head (loss terms + the gradients the network backward pass starts from), the KL-weight schedule and the optimiser step
-(global-norm clip + Adam, gradient all-reduce).  The backward pass through the networks is not built.
+(global-norm clip + Adam, gradient all-reduce), and `Trainer`: the forward + backward pass through the networks (csrc/tmjx_train.cuh).
 
 `compute_gae` mirrors `track_mjx/agent/mlp_ppo/losses.py:39-101`: same argument names and meaning, time-major `[T, B]` fp32 CUDA
 tensors in, `(vs, advantages)` out, computed by the `tmjx_gae` kernel (csrc/tmjx_policy.cu).  No CPU fallback.
@@ -143,15 +143,19 @@ class Adam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=params.device)
         self._scratch = torch.zeros(int(self.lib.tmjx_adam_scratch_floats()), dtype=torch.float32, device=params.device)
 
-    def step(self, grads, all_reduce: bool | None = None):
+    def step(self, grads, all_reduce: bool | None = None, grad_scale: float | None = None):
+        """`grads` is all-reduced IN PLACE (it holds the SUM over ranks afterwards; the 1 / world_size of `pmean` is applied inside the
+        kernel, not to the buffer).  A caller that has already all-reduced (e.g. bucket by bucket, overlapped with the backward pass)
+        passes `all_reduce=False, grad_scale=1 / world_size`."""
         t = self.torch
-        if grads.shape != self.params.shape or grads.dtype != t.float32 or not grads.is_cuda:
-            raise ValueError("grads must be a float32 CUDA tensor shaped like params")
-        grads = grads.contiguous()
+        if grads.shape != self.params.shape or grads.dtype != t.float32 or not grads.is_cuda or grads.device != self.params.device:
+            raise ValueError("grads must be a float32 CUDA tensor shaped like params, on the same device")
+        if not grads.is_contiguous():
+            raise ValueError("grads must be contiguous (the all-reduce and the kernel work in place)")
         dist = t.distributed
         if all_reduce is None:
             all_reduce = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        scale = 1.0
+        scale = 1.0 if grad_scale is None else float(grad_scale)
         if all_reduce:
             dist.all_reduce(grads)
             scale = 1.0 / dist.get_world_size()
@@ -203,6 +207,8 @@ class RunningStatistics:
 
     def update(self, batch, all_reduce: bool | None = None):
         t, lib, D = self.torch, self.lib, self.D
+        if batch.device != self.mean.device:
+            raise ValueError(f"batch is on {batch.device}, the statistics on {self.mean.device}")
         x = batch.reshape(-1, D).to(t.float32).contiguous()
         n = int(x.shape[0])
         st = C.c_void_p(t.cuda.current_stream(x.device).cuda_stream)
@@ -225,3 +231,118 @@ class RunningStatistics:
             k = self._frozen[0].numel()
             self.mean[-k:].copy_(self._frozen[0]); self.std[-k:].copy_(self._frozen[1]); self.summed_variance[-k:].copy_(self._frozen[2])
         return self
+
+
+class _DevArray:
+    """A library-owned device buffer exposed through `__cuda_array_interface__` so that torch can alias it without a copy."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class Trainer:
+    """Forward + backward of the intention network and the value network for one PPO minibatch on the GPU (`tmjx_trainer_*`,
+    csrc/tmjx_train.cuh): the `jax.value_and_grad(loss_fn)` half of the reference's `gradient_update_fn` (`ppo.py:263-272, 621-623`).
+
+    `params` / `grads` are ONE flat fp32 CUDA tensor each (views of buffers the library owns): [policy vector | value vector], every
+    vector in the layout of `policy.flatten_params` / `ValueNetwork` (normaliser mean, std first; their gradient is zero), so the NCCL
+    all-reduce and `Adam.step` act on a single tensor.  After changing `params` (optimiser step, normaliser update) call `sync()`.
+    No CPU fallback."""
+
+    def __init__(self, cfg, policy_params, value_params, value_layers, max_rows: int, device: int = 0):
+        import numpy as np
+        import torch
+
+        from . import policy as P
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("Trainer needs a CUDA device: there is no CPU fallback")
+        self.torch, self.lib, self.cfg = torch, L.load(), cfg
+        self.device = torch.device("cuda", device)
+        self.max_rows, self.value_layers = int(max_rows), tuple(int(x) for x in value_layers)
+        pd = P.make_desc(cfg)
+        vd = L.ValueDescC()
+        vd.obs_size, vd.n_hidden_layers = int(cfg.obs_size), len(self.value_layers)
+        for i, n in enumerate(self.value_layers):
+            vd.hidden_layers[i] = n
+        flat_p = P.flatten_params(cfg, policy_params)
+        parts = [value_params["norm/mean"], value_params["norm/std"]]
+        for i in range(len(self.value_layers) + 1):
+            parts += [value_params[f"hidden_{i}/kernel"], value_params[f"hidden_{i}/bias"]]
+        flat_v = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32).ravel() for a in parts]))
+        self._t = C.c_void_p()
+        fp = C.POINTER(C.c_float)
+        with torch.cuda.device(self.device):
+            rc = self.lib.tmjx_trainer_create(C.byref(pd), C.byref(vd), flat_p.ctypes.data_as(fp), flat_v.ctypes.data_as(fp), device, self.max_rows,
+                                              C.byref(self._t))
+        self._check(rc, "tmjx_trainer_create")
+        self.n_params = int(self.lib.tmjx_trainer_param_count(self._t))
+        self.n_policy = int(self.lib.tmjx_trainer_policy_param_count(self._t))
+        pp, gp = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.tmjx_trainer_buffers(self._t, C.byref(pp), C.byref(gp)), "tmjx_trainer_buffers")
+        self.params = torch.as_tensor(_DevArray(pp.value, self.n_params), device=self.device)
+        self.grads = torch.as_tensor(_DevArray(gp.value, self.n_params), device=self.device)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
+
+    def _st(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _arg(self, x, shape):
+        t = self.torch
+        if x.dtype != t.float32 or not x.is_contiguous() or x.device != self.device or tuple(x.shape) != tuple(shape):
+            raise ValueError(f"expected a contiguous float32 tensor of shape {tuple(shape)} on {self.device}, got {tuple(x.shape)} {x.dtype} {x.device}")
+        return C.c_void_p(x.data_ptr())
+
+    def set_normalizer(self, mean, std):
+        """`normalizer_params` of both networks <- the running statistics (`ppo.py:357-383` hands the same state to policy and value)."""
+        D = self.cfg.obs_size
+        for base in (0, self.n_policy):
+            self.params[base:base + D].copy_(mean)
+            self.params[base + D:base + 2 * D].copy_(std)
+
+    def sync(self):
+        self._check(self.lib.tmjx_trainer_sync(self._t, self._st()), "tmjx_trainer_sync")
+
+    def policy_forward(self, obs, eps_latent):
+        t, c = self.torch, self.cfg
+        rows = int(obs.shape[0])
+        f = dict(dtype=t.float32, device=self.device)
+        logits, mean, logvar = t.empty(rows, 2 * c.action_size, **f), t.empty(rows, c.latent_size, **f), t.empty(rows, c.latent_size, **f)
+        self._check(self.lib.tmjx_trainer_policy_forward(self._t, self._arg(obs, (rows, c.obs_size)), self._arg(eps_latent, (rows, c.latent_size)), rows,
+                                                         C.c_void_p(logits.data_ptr()), C.c_void_p(mean.data_ptr()), C.c_void_p(logvar.data_ptr()),
+                                                         self._st()), "tmjx_trainer_policy_forward")
+        return logits, mean, logvar
+
+    def policy_backward(self, d_logits, d_latent_mean, d_latent_logvar):
+        c = self.cfg
+        rows = int(d_logits.shape[0])
+        self._check(self.lib.tmjx_trainer_policy_backward(self._t, self._arg(d_logits, (rows, 2 * c.action_size)),
+                                                          self._arg(d_latent_mean, (rows, c.latent_size)), self._arg(d_latent_logvar, (rows, c.latent_size)),
+                                                          rows, self._st()), "tmjx_trainer_policy_backward")
+
+    def value_forward(self, obs):
+        t = self.torch
+        rows = int(obs.shape[0])
+        v = t.empty(rows, dtype=t.float32, device=self.device)
+        self._check(self.lib.tmjx_trainer_value_forward(self._t, self._arg(obs, (rows, self.cfg.obs_size)), rows, C.c_void_p(v.data_ptr()), self._st()),
+                    "tmjx_trainer_value_forward")
+        return v
+
+    def value_backward(self, d_value):
+        rows = int(d_value.shape[0])
+        self._check(self.lib.tmjx_trainer_value_backward(self._t, self._arg(d_value, (rows,)), rows, self._st()), "tmjx_trainer_value_backward")
+
+    def close(self):
+        if getattr(self, "_t", None):
+            self.params = self.grads = None
+            self.lib.tmjx_trainer_destroy(self._t)
+            self._t = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -118,6 +118,11 @@ class IntentionPolicy:
                 eps_latent = t.randn(n, self.cfg.latent_size, device=self.device)
             if eps_action is None:
                 eps_action = t.randn(n, self.cfg.action_size, device=self.device)
+        for name, x, width in (("obs", obs, self.cfg.obs_size), ("eps_latent", eps_latent, self.cfg.latent_size), ("eps_action", eps_action, self.cfg.action_size)):
+            if x is not None and (x.dtype != t.float32 or not x.is_contiguous() or x.device != self.device or tuple(x.shape) != (n, width)):
+                raise ValueError(f"{name} must be a contiguous float32 [{n}, {width}] tensor on {self.device}")
+        if n > self.max_env:
+            raise ValueError(f"{n} rows exceed the policy's max_env = {self.max_env}")
         ptr = lambda x: None if x is None else C.c_void_p(x.data_ptr())
         o = self.out if out is None else {**self.out, **out}
         for k, v in o.items():
@@ -129,6 +134,19 @@ class IntentionPolicy:
         if rc != 0:
             raise RuntimeError(f"tmjx_policy_act failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
         return o["action"][:n], {k: v[:n] for k, v in o.items() if k != "action"}
+
+    def set_params(self, flat_params):
+        """Refresh the weights and the normaliser from a flat fp32 CUDA vector in `flatten_params` order (e.g. the policy slice of
+        `learner.Trainer.params` after an optimiser step): `tmjx_policy_set_params`, an in-place repack, no reallocation."""
+        t = self.torch
+        if flat_params.dtype != t.float32 or not flat_params.is_contiguous() or flat_params.device != self.device:
+            raise ValueError("flat_params must be a contiguous float32 tensor on the policy's device")
+        desc = make_desc(self.cfg)
+        if flat_params.numel() != self.lib.tmjx_policy_param_count(C.byref(desc)):
+            raise ValueError("flat parameter vector has the wrong length")
+        rc = self.lib.tmjx_policy_set_params(self._p, C.c_void_p(flat_params.data_ptr()), C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"tmjx_policy_set_params failed ({rc}): {self.lib.tmjx_policy_last_error().decode()}")
 
     def linear(self, which: int, x, y):
         rc = self.lib.tmjx_policy_linear(self._p, which, C.c_void_p(x.data_ptr()), int(x.stride(0)), C.c_void_p(y.data_ptr()), int(y.stride(0)),
@@ -196,7 +214,9 @@ class ValueNetwork:
         lead = tuple(obs.shape[:-1])
         x = obs.reshape(-1, self.obs_size).to(t.float32).contiguous()
         n = int(x.shape[0])
-        v = t.empty(n, dtype=t.float32, device=self.device) if out is None else out.reshape(-1)
+        if out is not None and (not out.is_contiguous() or out.dtype != t.float32 or out.numel() != n or out.device != self.device):
+            raise ValueError("out must be a contiguous float32 tensor with one element per observation row, on the network's device")
+        v = t.empty(n, dtype=t.float32, device=self.device) if out is None else out.view(-1)
         st = C.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
         for i in range(0, n, self.max_env):                          # row chunks of at most max_env (the activation buffers' size)
             m = min(self.max_env, n - i)
