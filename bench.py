@@ -61,7 +61,7 @@ def workload_config(n_gpus, workload="tracking"):
         "physics_steps_per_control_step": ea["physics_steps_per_control_step"], "solver": ea["solver"], "iterations": ea["iterations"],
         "ls_iterations": ea["ls_iterations"],
         "actions": ("tanh-normal samples of the seed-0 LeCun-uniform intention network on the env's own observations" if w["policy"]
-                    else "N(0,1) per step (clipped to ctrlrange by the actuator model)"),
+                    else "N(0,1) per step (clipped to ctrlrange by the actuator model); under the shipped CG 5/5 solve this law makes ~3 % of the env-steps end in NaN (nan_frac; profiles/r2_blowup_bisect.txt), which the reference's NaN => done rule and the auto-reset absorb"),
         "l2": "flushed between timed iterations",
         "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
     }
@@ -197,7 +197,7 @@ def run_ours(args, rank, world, local_rank):
                 torch.randn(ENVS_PER_GPU, pcfg.action_size, device=dev, generator=gen)) for _ in range(min(n_act, 8))]
         acts = None
     else:
-        acts = [torch.randn(ENVS_PER_GPU, env.action_size, device=dev, generator=gen) for _ in range(n_act)]
+        acts = [args.action_scale * torch.randn(ENVS_PER_GPU, env.action_size, device=dev, generator=gen) for _ in range(n_act)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def next_action(i, st):
@@ -224,6 +224,7 @@ def run_ours(args, rank, world, local_rank):
     wall0 = time.perf_counter()
     rew_sum = torch.zeros((), device=dev)
     done_sum = torch.zeros((), device=dev)
+    nan_sum = torch.zeros((), device=dev)
     for i in range(K):
         flush.zero_()
         evs[i][0].record()
@@ -233,6 +234,7 @@ def run_ours(args, rank, world, local_rank):
         evs[i][2].record()
         rew_sum += state.reward.sum()
         done_sum += state.done.sum()
+        nan_sum += state.metrics["nan"].sum()
     barrier()
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(c) for a, _, c in evs)
@@ -240,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
     pol_ms = sum(a.elapsed_time(b) for a, b, _ in evs)       # the policy kernels (0 launches for random actions)
     clocks = sampler.stop() if rank == 0 else None
     max_ms = max_over_ranks(dev_ms, dev, shard)                      # device time, max over ranks
-    stats = reduce_episode_stats(rew_sum, done_sum, K, shard)        # SUM over NVLink: the only collective of the env path
+    stats = reduce_episode_stats(rew_sum, done_sum, K, shard, nan_sum=nan_sum)   # SUM over NVLink: the only collective of the env path
     value = ENVS_PER_GPU * world * K / (max_ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step
@@ -335,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline and args.workload == "tracking":
-        cpu_baseline = cpu_baseline_leg(walker, clips, config)
+        cpu_baseline = cpu_baseline_leg(walker, clips, config, full=args.full_cpu_baseline)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
@@ -463,8 +465,9 @@ def run_ppo(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def cpu_baseline_leg(walker, clips, config):
-    """The oracle port on the host cores of this box, bounded to ~10-20 s."""
+def cpu_baseline_leg(walker, clips, config, full=False):
+    """The oracle port on the host cores of this box, bounded to ~10-20 s; `full`: BASELINE configs[0] at its stated length
+    (64 envs, random actions, 1000 control steps; about two minutes on 16 cores)."""
     import numpy as np
 
     import common
@@ -475,7 +478,8 @@ def cpu_baseline_leg(walker, clips, config):
     cfg = config.make_task_config(walker, config.RewardConfig(), **env_args)
     cores = os.cpu_count() or 1
     orc = Oracle(walker.blob, cfg, clips, dtype=np.float32, nthreads=cores)
-    sample = min(ENVS_PER_GPU, max(64, 4 * cores))
+    sample = 64 if full else min(ENVS_PER_GPU, max(64, 4 * cores))
+    max_steps, max_s = (1000, 1e9) if full else (50, 10.0)
     buf = orc.alloc(sample, debug=False)
     common.put(buf, common.init_buffers(buf, clips, seed=0))
     orc.forward(buf, L.TMJX_F_SNAPSHOT)
@@ -483,7 +487,7 @@ def cpu_baseline_leg(walker, clips, config):
     orc.step(buf, rng.normal(size=(sample, walker.nu)).astype(np.float32), L.TMJX_F_AUTORESET)
     t0 = time.perf_counter()
     steps = 0
-    while time.perf_counter() - t0 < 10.0 and steps < 50:
+    while time.perf_counter() - t0 < max_s and steps < max_steps:
         orc.step(buf, rng.normal(size=(sample, walker.nu)).astype(np.float32), L.TMJX_F_AUTORESET)
         steps += 1
     dt = time.perf_counter() - t0
@@ -517,6 +521,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="tracking", choices=sorted(WORKLOADS) + ["ppo"],
                     help="tracking = BASELINE configs[1] (the bench line); intention = configs[2]; ppo = configs[3]; contact = configs[4]")
+    ap.add_argument("--action-scale", type=float, default=1.0, help="std of the random actions (default 1.0 = the N(0,1) law of SURVEY 8d)")
+    ap.add_argument("--full-cpu-baseline", action="store_true", help="cpu_baseline = BASELINE configs[0] at its stated length: 64 envs x 1000 steps")
     ap.add_argument("--ppo-envs", type=int, default=65536, help="global number of envs of the ppo workload (split over the GPUs)")
     ap.add_argument("--ppo-clips", type=int, default=842)
     args = ap.parse_args()

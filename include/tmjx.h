@@ -167,6 +167,9 @@ const char* tmjx_last_error(void);
 int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg, int device, TmjxModel** out);
 void tmjx_model_destroy(TmjxModel* m);
 int tmjx_model_dims(const TmjxModel* m, TmjxDims* out);
+/* brax EpisodeWrapper limit of the fused wrappers (`wrappers.wrap(env, episode_length=...)`, wrappers.py:18-56): synchronous, takes
+ * effect for every later tmjx_step with TMJX_F_AUTORESET. */
+int tmjx_model_set_episode_length(TmjxModel* m, int episode_length);
 
 /* Reference clips: HOST pointers to the eight ReferenceClip fields (io/load.py:16-38), each
  * `[n_clips, clip_len, d]` fp32 row-major. The hot subset is packed into one device table. */
@@ -298,6 +301,22 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
 size_t tmjx_adam_scratch_floats(void);
 int tmjx_adam_step(float* params, const float* grads, float* mu, float* nu, size_t n, float learning_rate, float b1, float b2, float eps,
                    float max_grad_norm, float grad_scale, int count, float* grad_norm_out, float* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * XLA-FFI custom-call handlers (csrc/tmjx_xla_ffi.cc): what `jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(lib.tmjx_step_ffi),
+ * platform="CUDA")` binds so that the step stays inside `jit` / `lax.scan` / `pmap` like the reference's env (ppo.py:333-340, 409).
+ * They decode XLA's call frame (operands: [action,] the 25 TmjxState leaves, donated; results: the same 25 leaves, then obs, reward,
+ * done, metrics, cur_frame; attributes: model, clips, flags as int64) and forward to tmjx_step / tmjx_forward on XLA's stream.
+ * tmjx_xla_ffi_available() is 1 when the library was built against jaxlib's own xla/ffi/api/c_api.h, 0 when against the recalled
+ * subset shipped next to the adapter; tmjx_ffi_selftest builds a call frame by hand and runs a handler through it (tests). */
+struct XLA_FFI_CallFrame;
+struct XLA_FFI_Error;
+struct XLA_FFI_Error* tmjx_step_ffi(struct XLA_FFI_CallFrame* call_frame);
+struct XLA_FFI_Error* tmjx_forward_ffi(struct XLA_FFI_CallFrame* call_frame);
+int tmjx_xla_ffi_available(void);
+int tmjx_ffi_selftest(int is_step, const void* model, const void* clips, const float* action, int nu, const TmjxState* s, const TmjxOut* o,
+                      const int* state_dims, const int* state_is_int, const int* out_dims, int n_env, unsigned flags, void* stream, int alias);
+const char* tmjx_ffi_selftest_error(void);
 
 /* Refresh an acting policy (tmjx_policy_create) or value network (tmjx_value_create) from a flat DEVICE parameter vector in the layout
  * of its create call (normaliser mean, std first): the hand-off from the learner to the actor after every optimiser / normaliser

@@ -57,7 +57,7 @@ def main():
     ms = timed(lambda: ppo_loss_head(logits, mu, lv, v, bv, r, disc, tr, raw, blp, eps), reps=20)
     # every input once (2A + A + A + 2L + 6 floats per row) + every output once (2A + 2L + 3)
     gb = T * B * (4 * A + 2 * Lz + 6 + 2 * A + 2 * Lz + 3) * 4 / 1e9
-    out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 6}
+    out["ppo_loss_head"] = {"T": T, "B": B, "A": A, "L": Lz, "ms": ms, "algorithmic_GB": gb, "GBps": gb / (ms * 1e-3), "launches": 6, "two_pass": bool(int(os.environ.get("TMJX_PPO_TWO_PASS", "0")))}
     # optimiser step over the intention network's parameter count (2.6 M: L2-resident) and over 256 Mi parameters (HBM-bound)
     for name, n in (("adam_2p6M", 2_600_000), ("adam_256M", 1 << 28)):
         if QUICK and n > 1 << 24:
@@ -77,6 +77,11 @@ def main():
     ms = timed(lambda: net.apply(xo), reps=5)
     fl = rows * 2.0 * (D * 1024 + 1024 * 1024 + 1024)
     out["value_network"] = {"rows": rows, "ms": ms, "algorithmic_TFLOP": fl / 1e12, "TFLOPs": fl / 1e12 / (ms * 1e-3)}
+    critic = (512, 512, 512, 512, 512, 256)                  # critic_layer_sizes of config/rodent-full-clips.yaml:54 (the shipped value network)
+    net2 = ValueNetwork(D, init_value_params(D, critic), max_env=B, hidden_layers=critic)
+    ms = timed(lambda: net2.apply(xo), reps=5)
+    fl = rows * 2.0 * (D * 512 + 4 * 512 * 512 + 512 * 256 + 256)
+    out["value_network_shipped_critic"] = {"rows": rows, "hidden": list(critic), "ms": ms, "algorithmic_TFLOP": fl / 1e12, "TFLOPs": fl / 1e12 / (ms * 1e-3)}
     out["peaks"] = {k: peaks.get(k) for k in ("hbm_gbs", "gpu_name")}
     print(json.dumps(out))
 

@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.tmjx_model_destroy.argtypes = [vp]
     lib.tmjx_model_destroy.restype = None
     lib.tmjx_model_dims.argtypes = [vp, C.POINTER(DimsC)]
+    lib.tmjx_model_set_episode_length.argtypes = [vp, i32]
     lib.tmjx_clips_create.argtypes = [vp] + [fp] * 8 + [i32, i32, i32, C.POINTER(vp)]
     lib.tmjx_clips_destroy.argtypes = [vp]
     lib.tmjx_clips_destroy.restype = None
@@ -143,6 +144,9 @@ def load() -> C.CDLL:
     lib.tmjx_adam_step.argtypes = [vp, vp, vp, vp, sz] + [C.c_float] * 6 + [i32, vp, vp, vp]
     lib.tmjx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, vp]
     lib.tmjx_policy_set_params.argtypes = [vp, vp, vp]
+    lib.tmjx_xla_ffi_available.restype = i32
+    lib.tmjx_ffi_selftest.argtypes = [i32, vp, vp, vp, i32, C.POINTER(StateC), C.POINTER(OutC), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, u32, vp, i32]
+    lib.tmjx_ffi_selftest_error.restype = C.c_char_p
     lib.tmjx_trainer_create.argtypes = [C.POINTER(PolicyDescC), C.POINTER(ValueDescC), fp, fp, i32, i32, C.POINTER(vp)]
     lib.tmjx_trainer_destroy.argtypes = [vp]
     lib.tmjx_trainer_destroy.restype = None

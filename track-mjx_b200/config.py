@@ -112,8 +112,11 @@ class TaskConfigC(C.Structure):
 
 
 def episode_length(clip_length: int, random_init_range: int, traj_length: int, steps_for_cur_frame: float) -> int:
-    """reference track_mjx/train.py:221-225."""
-    return int((clip_length - random_init_range - traj_length) * steps_for_cur_frame)
+    """reference track_mjx/train.py:221-225 keeps the FLOAT product and brax's EpisodeWrapper truncates when `steps >= episode_length`
+    with an integer-valued step counter: the first step that satisfies it is ceil(limit), which is what the kernel compares against."""
+    import math
+
+    return int(math.ceil((clip_length - random_init_range - traj_length) * steps_for_cur_frame - 1e-9))
 
 
 def make_task_config(

@@ -352,7 +352,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 template <int BN2>
 __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
                                                                      const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
-                                                                     int act) {
+                                                                     int act, int nk_per_split = 0, size_t y_split_stride = 0) {
   using C3 = V3<BN2>;
   constexpr int BM2 = C3::BM2, STG = C3::STG;
   extern __shared__ uint8_t smem_raw[];
@@ -360,7 +360,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
-  const int nk = Kpad / BK;
+  // split-K (the wgrad GEMMs of the backward pass: small M x N, K = the minibatch rows): block z accumulates K slices
+  // [z nk_per_split, (z + 1) nk_per_split) into its own output plane Y + z y_split_stride; the planes are summed in z order later
+  int nk = Kpad / BK, kt0 = 0;
+  if (nk_per_split > 0) {
+    kt0 = int(blockIdx.z) * nk_per_split;
+    nk = min(nk_per_split, nk - kt0);
+    Y += size_t(blockIdx.z) * y_split_stride;
+  }
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t kTmemCols = 2 * BN2;
 
@@ -391,8 +398,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
       asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(&bar_full[s])),
                    "r"(uint32_t(C3::kStage))
                    : "memory");
-      tma_load_2d(sa, &mapX, kt * BK, m0, &bar_full[s]);
-      tma_load_2d(sb, &mapW, kt * BK, n0, &bar_full[s]);
+      tma_load_2d(sa, &mapX, (kt0 + kt) * BK, m0, &bar_full[s]);
+      tma_load_2d(sb, &mapW, (kt0 + kt) * BK, n0, &bar_full[s]);
     }
   } else if (tid == 32) {
     // ---- MMA issuer
@@ -680,7 +687,7 @@ __global__ void __launch_bounds__(256) ppo_reduce_kernel(const double* __restric
                                                          PpoHyper hp, float* __restrict__ out) {
   __shared__ double sh[256];
   double tot[kPpoSums];
-  const int nsum = stage == 1 ? kPpoSums : 1;
+  const int nsum = (stage == 1 || stage == 3) ? kPpoSums : (stage == 0 ? 2 : 1);
   for (int k = 0; k < nsum; ++k) {
     double s = 0.0;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[size_t(b) * kPpoSums + k];
@@ -695,7 +702,25 @@ __global__ void __launch_bounds__(256) ppo_reduce_kernel(const double* __restric
   }
   if (threadIdx.x != 0) return;
   const double n = double(T) * B;
-  if (stage == 1) {
+  if (stage == 0) {                                                 // one-pass path: advantage statistics only (slots 0, 1)
+    float mean = 0.f, stdv = 1.f, inv = 1.f;
+    if (hp.normalize_advantage) {
+      const double m = tot[0] / n;
+      mean = float(m);
+      stdv = float(sqrt(fmax(tot[1] / n - m * m, 0.0)));
+      inv = 1.f / (stdv + 1e-8f);
+    }
+    out[5] = mean; out[6] = stdv; out[7] = inv;
+  } else if (stage == 3) {                                          // one-pass path: every loss term (slot 0 = surrogate sum, 2..5 as stage 1)
+    const float kl0 = float(tot[3] / (double(B) * L));
+    float klat = hp.kl_weight * kl0;
+    if (T > 1) klat = hp.kl_weight * ((kl0 + float(tot[4] / (double(T - 1) * B * L)) * float(T - 1)) / float(T));
+    out[2] = float(tot[5] / n) * 0.5f * 0.5f;
+    out[3] = klat;
+    out[4] = hp.entropy_cost * -float(tot[2] / n);
+    out[1] = -float(tot[0] / n);
+    out[0] = out[1] + out[2] + out[4] + out[3];
+  } else if (stage == 1) {
     float mean = 0.f, stdv = 1.f, inv = 1.f;
     if (hp.normalize_advantage) {                                   // :175-176 (population standard deviation)
       const double m = tot[0] / n;
@@ -767,6 +792,105 @@ __global__ void __launch_bounds__(32 * kPpoWarps) ppo_grad_kernel(const float* _
     }
   }
   block_partials(acc, 1, partial);
+}
+
+// One-pass loss head (default).  The advantage statistics only need the GAE output, so they are reduced first (adv_stats_kernel over
+// the 4-byte-per-row advantage array); the row kernel then reads every input ONCE and writes every gradient once: per row group
+// (8 lanes) the action terms are kept in registers between the log-prob sum and the gradient that needs it (rho = exp(logp - behaviour)).
+// DRAM traffic = the algorithmic 1.9 KB per row (the two-pass form read the inputs twice: 1.76 x).
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, size_t n, double* __restrict__ partial) {
+  __shared__ double sh[2][8];
+  double a = 0.0, a2 = 0.0;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) { const double v = adv[i]; a += v; a2 += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    partial[size_t(blockIdx.x) * kPpoSums + threadIdx.x] = t;
+  }
+}
+
+constexpr int kPpoMaxPerLane = 8;   // action elements per lane of a row group: A <= 64
+__global__ void __launch_bounds__(32 * kPpoWarps) ppo_fused_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
+                                                        const float* __restrict__ eps, const float* __restrict__ lat_mean,
+                                                        const float* __restrict__ lat_logvar, const float* __restrict__ baseline,
+                                                        const float* __restrict__ vs, const float* __restrict__ behaviour_logp,
+                                                        const float* __restrict__ stats, int T, int B, int A, int L, PpoHyper hp,
+                                                        const float* __restrict__ adv_raw, float* __restrict__ advantages,
+                                                        float* __restrict__ d_logits, float* __restrict__ d_mean, float* __restrict__ d_logvar,
+                                                        float* __restrict__ d_baseline, double* __restrict__ partial) {
+  const size_t nrow = size_t(T) * B, stride = size_t(gridDim.x) * kPpoWarps * kPpoRowsPerWarp;
+  const int lane = threadIdx.x & (kPpoLanes - 1);
+  const float inv_n = 1.f / float(nrow), adv_mean = stats[5], adv_inv = stats[7];
+  const float ce = -hp.entropy_cost * inv_n;
+  const float w = hp.kl_weight / (float(T) * float(B) * float(L));
+  const float kLogPriorVar = logf(kArPriorVar);
+  double acc[kPpoSums] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // 0 surrogate, 2 entropy, 3 kl_0, 4 kl_t, 5 (vs - baseline)^2
+  for (size_t row0 = (size_t(blockIdx.x) * kPpoWarps + (threadIdx.x >> 5)) * kPpoRowsPerWarp; row0 < nrow; row0 += stride) {
+    const size_t row = row0 + ((threadIdx.x & 31) / kPpoLanes);
+    const bool live = row < nrow;
+    const int t = live ? int(row / B) : 0;
+    float lp = 0.f, en = 0.f, k = 0.f;
+    float r_z[kPpoMaxPerLane], r_rs[kPpoMaxPerLane], r_dj[kPpoMaxPerLane], r_sig[kPpoMaxPerLane], r_e[kPpoMaxPerLane];
+    if (live) {
+      const float* lg = logits + row * 2 * A;
+#pragma unroll
+      for (int q = 0; q < kPpoMaxPerLane; ++q) {
+        const int i = lane + q * kPpoLanes;
+        if (i < A) {
+          const float loc = lg[i], sr = lg[A + i], scale = softplus(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
+          const float z = (raw - loc) / scale, ls = logf(scale), x = fmaf(scale, e, loc);
+          lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh(raw);
+          en += 0.5f + 0.91893853320467274f + ls + log_det_tanh(x);
+          r_z[q] = z; r_rs[q] = 1.f / scale; r_dj[q] = -2.f * tanhf(x); r_sig[q] = 1.f / (1.f + expf(-sr)); r_e[q] = e;
+        }
+      }
+      const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L, *mn = mu + size_t(B) * L;
+      for (int j = lane; j < L; j += kPpoLanes) {
+        const float m = mu[j], v = lv[j], ev = expf(v);
+        float gm, gv;
+        if (t == 0) {
+          k += 1.f + v - m * m - ev;
+          gm = m; gv = -0.5f * (1.f - ev);
+        } else {
+          const float dm = kArAlpha * mp[j] - m;
+          k += (ev + dm * dm) * kArInvPriorVar - 1.f + (kLogPriorVar - v);
+          gm = -dm * kArInvPriorVar; gv = 0.5f * (ev * kArInvPriorVar - 1.f);
+        }
+        if (t + 1 < T) gm += kArAlpha * (kArAlpha * m - mn[j]) * kArInvPriorVar;
+        d_mean[row * L + j] = w * gm;
+        d_logvar[row * L + j] = w * gv;
+      }
+    }
+    lp = group_sum(lp); en = group_sum(en); k = group_sum(k);
+    if (!live) continue;
+    const float a = (adv_raw[row] - adv_mean) * adv_inv, rho = expf(lp - behaviour_logp[row]);
+    const float clipped = fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon);
+    const float s1 = rho * a, s2 = clipped * a;
+    const float cp = (s1 <= s2) ? -a * rho * inv_n : 0.f;
+    float* dl = d_logits + row * 2 * A;
+#pragma unroll
+    for (int q = 0; q < kPpoMaxPerLane; ++q) {
+      const int i = lane + q * kPpoLanes;
+      if (i < A) {
+        dl[i] = cp * (r_z[q] * r_rs[q]) + ce * r_dj[q];
+        dl[A + i] = (cp * ((r_z[q] * r_z[q] - 1.f) * r_rs[q]) + ce * (r_rs[q] + r_dj[q] * r_e[q])) * r_sig[q];
+      }
+    }
+    if (lane == 0) {
+      const double e = double(vs[row]) - double(baseline[row]);
+      d_baseline[row] = -0.5f * (vs[row] - baseline[row]) * inv_n;
+      advantages[row] = a;
+      acc[0] += double(fminf(s1, s2));
+      acc[2] += en;
+      if (t == 0) acc[3] += -0.5 * double(k); else acc[4] += 0.5 * double(k);
+      acc[5] += e * e;
+    }
+  }
+  block_partials(acc, kPpoSums, partial);
 }
 
 // ---- Optimiser step (reference ppo.py:517-520: optax.chain(clip_by_global_norm(10.0), adam(lr)), optax 0.2.5) -------------
@@ -1365,6 +1489,18 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
   ppo_prep_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(reward, discount, truncation, hp.reward_scaling, rewards, termination, n);
   gae_kernel<<<(B + 127) / 128, 128, 0, st>>>(truncation, termination, rewards, baseline, bootstrap_value, hp.gae_lambda, hp.discounting, vs,
                                               adv_raw, T, B);
+  static const bool two_pass = [] { const char* e = std::getenv("TMJX_PPO_TWO_PASS"); return e && atoi(e); }();   // A/B knob: the round-1 form
+  if (!two_pass && A <= kPpoLanes * kPpoMaxPerLane) {
+    const int nb0 = int(std::min<size_t>(kPpoBlocks, (n + 255) / 256));
+    adv_stats_kernel<<<nb0, 256, 0, st>>>(adv_raw, n, partial);
+    ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nb0, 0, T, B, L, hp, losses);
+    ppo_fused_kernel<<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, behaviour_log_prob,
+                                                       losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean, d_latent_logvar,
+                                                       d_baseline, partial);
+    ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 3, T, B, L, hp, losses);
+    PCU(cudaGetLastError());
+    return TMJX_OK;
+  }
   ppo_rows_kernel<<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, adv_raw, vs, baseline, T, B,
                                                     A, L, logp, partial);
   ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, T, B, L, hp, losses);

@@ -1836,7 +1836,8 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
     for (int k = 0; k < kRowSlots; ++k) bad |= isnan(fo.so.force[k]);
     bad = __any_sync(FULLMASK, bad);
 
-    const int clip = a.st.clip_idx[e], sf = a.st.start_frame[e];
+    // jnp gathers clamp out-of-range indices (x[info["clip_idx"]], multi_clip_tracking.py:98-109): so does the table lookup here
+    const int clip = min(max(a.st.clip_idx[e], 0), a.n_clips - 1), sf = a.st.start_frame[e];
     const int frame = cur_frame_of(time, cfg.mocap_hz, sf);
     float* obs = a.out.obs + size_t(e) * nobs;
     float done = 0.f;
@@ -2222,6 +2223,15 @@ void tmjx_model_destroy(TmjxModel* m) {
   cudaSetDevice(m->device);
   cudaFree(m->d_i32); cudaFree(m->d_u16); cudaFree(m->d_u8); cudaFree(m->d_f32); cudaFree(m->d_task); cudaFree(m->d_spill);
   delete m;
+}
+
+int tmjx_model_set_episode_length(TmjxModel* m, int episode_length) {
+  if (!m || episode_length <= 0) return fail(TMJX_E_ARG, "episode_length must be positive");
+  CU(cudaSetDevice(m->device));
+  m->cfg.episode_length = episode_length;
+  m->task.cfg.episode_length = episode_length;
+  CU(cudaMemcpy(m->d_task, &m->task, sizeof(DevTask), cudaMemcpyHostToDevice));   // synchronous: ordered against every stream's later launches
+  return TMJX_OK;
 }
 
 int tmjx_model_dims(const TmjxModel* m, TmjxDims* d) {

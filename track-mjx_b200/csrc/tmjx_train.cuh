@@ -21,7 +21,8 @@ namespace tmjx_policy {
 
 constexpr int kTrainLd = 1024;       // row pitch of the gradient-activation buffers (widest layer / padded fan-in)
 constexpr int kBwdWarps = 4;         // warps per block of the row kernels (4 x 3 x 1024 floats of column accumulators = 48 KB)
-constexpr int kBwdBlocks = 592;      // 4 x 148: partial column sums per block, reduced in block order
+constexpr int kBwdBlocks = 296;      // 2 x 148: partial column sums per block, reduced in a fixed order
+constexpr int kWgradMaxSplits = 64;  // split-K planes of the wgrad GEMM (scratch: kWgradMaxSplits x the largest padded kernel)
 
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
@@ -136,27 +137,44 @@ __global__ void __launch_bounds__(32 * kBwdWarps) ln_silu_bwd_kernel(const float
   }
 }
 
-// column sums of a plain [M, ld] matrix (d bias of the linear heads): per-block partials in the same layout (slot 0 only)
+// column sums of a plain [M, ld] matrix (d bias of the linear heads): per-block partials in the same layout (slot 0 only).
+// Block = 32 columns x 8 row lanes; rows strided over (blockIdx.y, row lane); the 8 row lanes are added in lane order.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, int ld, int n, int npad, float* __restrict__ partial, int M) {
-  // thread = column (coalesced over columns), rows strided over blockIdx.y
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int r = blockIdx.y; r < M; r += gridDim.y) t += X[size_t(r) * ld + c];
-  partial[size_t(blockIdx.y) * 3 * npad + c] = t;
+  if (c < n)
+    for (int r = blockIdx.y * 8 + ty; r < M; r += gridDim.y * 8) t += X[size_t(r) * ld + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += red[j][tx];
+    partial[size_t(blockIdx.y) * 3 * npad + c] = a;
+  }
 }
 
-// out_k[c] = sum over blocks (in block order) of partial[b][k][c], k = 0 (d bias), 1 (d LN scale), 2 (d LN bias); a destination may
-// be null.  The fused (mean | logvar) head splits slot 0 between two bias vectors at column n1.
-__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int nblk, int n, int npad, int n1, float* __restrict__ d_bias,
-                                     float* __restrict__ d_bias2, float* __restrict__ d_lns, float* __restrict__ d_lnb) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-  if (c >= n) return;
+// out_k[c] = sum over blocks (fixed order) of partial[b][k][c], k = 0 (d bias), 1 (d LN scale), 2 (d LN bias); a destination may
+// be null.  The fused (mean | logvar) head splits slot 0 between two bias vectors at column n1.  Block = 32 columns x 8 lanes over
+// the partial blocks (lane j adds blocks j, j + 8, ... in order, the 8 lanes are added in lane order).
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int nblk, int n, int npad, int n1,
+                                                            float* __restrict__ d_bias, float* __restrict__ d_bias2, float* __restrict__ d_lns,
+                                                            float* __restrict__ d_lnb) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx, k = blockIdx.y;
+  float t = 0.f;
+  if (c < n)
+    for (int b = ty; b < nblk; b += 8) t += partial[(size_t(b) * 3 + k) * npad + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty != 0 || c >= n) return;
   float* dst = k == 0 ? (c < n1 ? d_bias : d_bias2) : (k == 1 ? d_lns : d_lnb);
   if (!dst) return;
-  float t = 0.f;
-  for (int b = 0; b < nblk; ++b) t += partial[(size_t(b) * 3 + k) * npad + c];
-  dst[k == 0 && c >= n1 ? c - n1 : c] = t;
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a += red[j][tx];
+  dst[k == 0 && c >= n1 ? c - n1 : c] = a;
 }
 
 // dst[c, r] = src[r, c] for r < M, c < ncols (32 x 32 tiles through shared memory); columns r in [M, Mpad) of dst are zeroed
@@ -176,12 +194,15 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
-// wgrad scratch [k, ld] -> the flat gradient vector: kernel [k, n1] (and [k, n - n1] for the second half of the fused head)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dWs, int ld, int k, int n, int n1, float* __restrict__ g1, float* __restrict__ g2) {
+// wgrad scratch (`planes` split-K planes of [k, ld], summed in plane order) -> the flat gradient vector: kernel [k, n1] (and
+// [k, n - n1] for the second half of the fused head)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dWs, int ld, size_t plane_stride, int planes, int k, int n, int n1,
+                                    float* __restrict__ g1, float* __restrict__ g2) {
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= size_t(k) * n) return;
   const int i = int(idx / n), j = int(idx % n);
-  const float v = dWs[size_t(i) * ld + j];
+  float v = 0.f;
+  for (int z = 0; z < planes; ++z) v += dWs[size_t(z) * plane_stride + size_t(i) * ld + j];
   if (j < n1) g1[size_t(i) * n1 + j] = v;
   else g2[size_t(i) * (n - n1) + (j - n1)] = v;
 }
@@ -257,19 +278,27 @@ struct TmjxTrainer {
   float* dA[2] = {nullptr, nullptr};   // gradient w.r.t. a layer's output, ping-pong [max_rows, kTrainLd]
   float* dH = nullptr;                 // gradient w.r.t. a layer's pre-activation [max_rows, kTrainLd]
   float *xT = nullptr, *dhT = nullptr; // transposed operands of the wgrad GEMM [kTrainLd, rows_ld]
-  float* dWs = nullptr;                // wgrad output [kTrainLd, kTrainLd]
+  float* dWs = nullptr;                // wgrad output: split-K planes of [kpad, npad]
   float *zeros = nullptr, *partial = nullptr, *eps = nullptr;
   std::vector<void*> owned;
 };
 
+// splits > 1: split-K into `splits` output planes of plane_stride floats (see linear_tf32_tma_kernel); *splits_out = planes written
 static int train_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const float* bias, float* Y, int ldy, int M, int Kpad, int Npad,
-                      cudaStream_t st) {
+                      cudaStream_t st, int splits = 1, size_t plane_stride = 0, int* splits_out = nullptr) {
+  int nk_per = 0, nz = 1;
+  if (splits > 1) {
+    const int nk = Kpad / BK;
+    nk_per = (nk + splits - 1) / splits;
+    nz = (nk + nk_per - 1) / nk_per;
+  }
+  if (splits_out) *splits_out = nz;
   if (Npad >= 512) {
-    dim3 grid((M + 255) / 256, Npad / 256);
-    linear_tf32_tma_kernel<256><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0);
+    dim3 grid((M + 255) / 256, Npad / 256, nz);
+    linear_tf32_tma_kernel<256><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
   } else {
-    dim3 grid((M + 255) / 256, Npad / 128);
-    linear_tf32_tma_kernel<128><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0);
+    dim3 grid((M + 255) / 256, Npad / 128, nz);
+    linear_tf32_tma_kernel<128><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
   }
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "GEMM launch failed");
 }
@@ -321,16 +350,16 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     if (L.act) {
       ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, size_t(kBwdWarps) * 3 * L.npad * 4, st>>>(t->dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale,
                                                                                             L.ln, t->dH, kTrainLd, t->partial, rows);
-      dim3 rg((L.n + 255) / 256, L.ln ? 3 : 1);
+      dim3 rg((L.n + 31) / 32, L.ln ? 3 : 1);
       colsum_reduce_kernel<<<rg, 256, 0, st>>>(t->partial, nblk, L.n, L.npad, L.n1, g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr,
                                                 L.ln ? g + L.off_lnb : nullptr);
       dh = t->dH;
       map_dh = &s.mapDH[l];
     } else {
-      const int ny = std::min(nblk, 128);
-      dim3 cg((L.n + 255) / 256, ny);
+      const int ny = std::min((rows + 7) / 8, 148);
+      dim3 cg((L.n + 31) / 32, ny);
       colsum_partial_kernel<<<cg, 256, 0, st>>>(dh, kTrainLd, L.n, L.npad, t->partial, rows);
-      colsum_reduce_kernel<<<dim3((L.n + 255) / 256, 1), 256, 0, st>>>(t->partial, ny, L.n, L.npad, L.n1, g + L.off_b,
+      colsum_reduce_kernel<<<dim3((L.n + 31) / 32, 1), 256, 0, st>>>(t->partial, ny, L.n, L.npad, L.n1, g + L.off_b,
                                                                         L.n1 < L.n ? g + L.off_b2 : nullptr, nullptr, nullptr);
     }
     // wgrad: dW = x^T dH
@@ -338,10 +367,15 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     const int ldx = l == 0 ? s.ldx0 : (*s.layers)[l - 1].npad;
     transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, t->xT, t->rows_ld);
     transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, t->dhT, t->rows_ld);
-    int rc = train_gemm(s.mapXT[l], s.mapDHT[l], t->zeros, t->dWs, kTrainLd, L.k, rows32, L.npad, st);
+    // split-K so that the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs: K = the minibatch rows is the long dimension
+    const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
+    const size_t plane = size_t(L.kpad) * L.npad, fit = (size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2) / plane;
+    const int want = std::max(1, std::min(std::min(kWgradMaxSplits, int(fit)), 148 / tiles));
+    int planes = 1;
+    int rc = train_gemm(s.mapXT[l], s.mapDHT[l], t->zeros, t->dWs, L.npad, L.k, rows32, L.npad, st, want, size_t(L.kpad) * L.npad, &planes);
     if (rc) return rc;
-    unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(t->dWs, kTrainLd, L.k, L.n, L.n1, g + L.off_w,
-                                                                                   L.n1 < L.n ? g + L.off_w2 : nullptr);
+    unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(t->dWs, L.npad, size_t(L.kpad) * L.npad, planes, L.k, L.n, L.n1,
+                                                                                   g + L.off_w, L.n1 < L.n ? g + L.off_w2 : nullptr);
     // dgrad: dx = dH W^T
     if (l > 0 || need_dx) {
       rc = train_gemm(*map_dh, s.mapWp[l], t->zeros, t->dA[*which ^ 1], kTrainLd, rows, L.npad, s.kNp[l], st);
@@ -402,7 +436,7 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
   for (int i = 0; i < 2; ++i) PCU(alloc(&t->dA[i], size_t(max_rows) * kTrainLd));
   PCU(alloc(&t->dH, size_t(max_rows) * kTrainLd));
   PCU(alloc(&t->xT, size_t(kTrainLd) * t->rows_ld)); PCU(alloc(&t->dhT, size_t(kTrainLd) * t->rows_ld));
-  PCU(alloc(&t->dWs, size_t(kTrainLd) * kTrainLd));
+  PCU(alloc(&t->dWs, size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2));   // planes x [kpad, npad]; kpad x npad <= 1024 x 512 for every layer here
   PCU(alloc(&t->zeros, kTrainLd)); PCU(alloc(&t->partial, size_t(kBwdBlocks) * 3 * kTrainLd));
   PCU(alloc(&t->eps, size_t(max_rows) * std::max(1, pd->latent_size)));
   PCU(cudaFuncSetAttribute(ln_silu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * kTrainLd * 4));

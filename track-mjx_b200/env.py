@@ -77,7 +77,9 @@ class Stepper:
         if not torch.cuda.is_available():
             raise RuntimeError("track_mjx_b200 needs a CUDA device: the env step has no CPU fallback")
         self.lib = L.load()
-        self.device = torch.device("cuda", device) if isinstance(device, int) else device
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.index is None:                      # torch.device("cuda") -> the current device, never None into ctypes
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_env = n_env
         self.cfg = cfg
         self._model = C.c_void_p()
@@ -144,6 +146,10 @@ class Stepper:
         self.buf["obs"] = obs
         self._out_c.obs = obs.data_ptr()
 
+    def set_episode_length(self, episode_length: int):
+        L.check(self.lib, self.lib.tmjx_model_set_episode_length(self._model, int(episode_length)), "tmjx_model_set_episode_length")
+        self.cfg.episode_length = int(episode_length)
+
     def clips_device_bytes(self) -> int:
         return int(self.lib.tmjx_clips_device_bytes(self._clips))
 
@@ -193,7 +199,10 @@ class MultiClipTracking:
         self._clip_pos = torch.from_numpy(np.ascontiguousarray(reference_clip.position)).to(self.device)
         self._clip_quat = torch.from_numpy(np.ascontiguousarray(reference_clip.quaternion)).to(self.device)
         self._clip_joints = torch.from_numpy(np.ascontiguousarray(reference_clip.joints)).to(self.device)
+        self._clip_dev = {"position": self._clip_pos, "quaternion": self._clip_quat, "joints": self._clip_joints}   # other fields on demand
         self._autoreset = False
+        self._snapshot_taken = False
+        self._mjx_model = walker          # the compiled model constants (the reference keeps `mjx.put_model(...)` here, single_clip_tracking.py:91)
 
     # ---- attributes callers use
     @property
@@ -228,7 +237,7 @@ class MultiClipTracking:
             clip_idx = torch.randint(0, self._n_clips, (n,), generator=g, device=self.device, dtype=torch.int32)
         elif not isinstance(clip_idx, torch.Tensor):
             clip_idx = torch.full((n,), int(clip_idx), device=self.device, dtype=torch.int32)
-        info = {"clip_idx": clip_idx.to(torch.int32), "start_frame": start_frame}
+        info = {"clip_idx": clip_idx.to(device=self.device, dtype=torch.int32), "start_frame": start_frame}
         return self.reset_from_clip(g, info, noise=True)
 
     def reset_from_clip(self, rng, info: dict[str, Any], noise: bool = True) -> State:
@@ -236,7 +245,13 @@ class MultiClipTracking:
         g = self._gen(rng)
         b = self.stepper.buf
         n, nq, nv = self.num_envs, self.stepper.dims["nq"], self.stepper.dims["nv"]
-        ci, sf = info["clip_idx"].long(), info["start_frame"].long()
+        # jnp indexing clamps out-of-range indices (the reference never raises at run time); an index that is not even integral is a bug
+        ci_in, sf_in = torch.as_tensor(info["clip_idx"], device=self.device), torch.as_tensor(info["start_frame"], device=self.device)
+        if ci_in.is_floating_point() or sf_in.is_floating_point() or ci_in.numel() not in (1, n) or sf_in.numel() not in (1, n):
+            raise ValueError("info['clip_idx'] / info['start_frame'] must be integer tensors with one entry per env (or one for all)")
+        ci = ci_in.reshape(-1).expand(n).long().clamp(0, self._n_clips - 1)
+        sf = sf_in.reshape(-1).expand(n).long().clamp(0, self._clip_pos.shape[1] - 1)
+        info = dict(info, clip_idx=ci.to(torch.int32), start_frame=sf.to(torch.int32))
         new_qpos = torch.cat([self._clip_pos[ci, sf], self._clip_quat[ci, sf], self._clip_joints[ci, sf]], dim=-1)
         s = self._reset_noise_scale
         # the reference draws qpos and qvel noise from the SAME key (:153-161): the first nv qvel draws equal the qpos draws
@@ -246,10 +261,14 @@ class MultiClipTracking:
         b["clip_idx"].copy_(info["clip_idx"].view(n, 1))
         b["start_frame"].copy_(info["start_frame"].view(n, 1))
         self.stepper.forward(L.TMJX_F_SNAPSHOT if self._autoreset else 0)
+        self._snapshot_taken = self._autoreset
         return self._state()
 
     def step(self, state: State, action: torch.Tensor) -> State:
         """reference single_clip_tracking.py:207-320 (+ fused wrappers after `wrap`)."""
+        if self._autoreset and not self._snapshot_taken:
+            raise RuntimeError("wrap(env) was applied after the last reset: the auto-reset wrapper has no first_* snapshot to restore "
+                               "(the reference takes it in the wrapper's reset, wrappers.py:281-286); call env.reset(...) again")
         self.stepper.step(action, L.TMJX_F_AUTORESET if self._autoreset else 0)
         return self._state()
 
@@ -265,12 +284,64 @@ class MultiClipTracking:
             "reference_obs_size": self.stepper.dims["reference_obs_size"],
             "proprioceptive_obs_size": self.stepper.dims["proprioceptive_obs_size"],
         }
+        info["reference_frame"] = ReferenceFrameView(self, info["clip_idx"], info["cur_frame"])     # lazy: gathered only when read
         if self._autoreset:
             info.update(steps=b["steps"][:, 0], truncation=b["truncation"][:, 0])
         return State(ps, b["obs"], b["reward"][:, 0], b["done"][:, 0], metrics, info)
 
+    def _clip_field(self, name: str) -> torch.Tensor:
+        """Device copy of one ReferenceClip field `[n_clips, clip_len, ...]`, uploaded on first use (the step kernel has its own packed table)."""
+        if name not in self._clip_dev:
+            self._clip_dev[name] = torch.from_numpy(np.ascontiguousarray(getattr(self._reference_clips, name), np.float32)).to(self.device)
+        return self._clip_dev[name]
+
     def _get_reference_clip(self, info) -> ReferenceClip:
-        return self._reference_clips
+        """reference multi_clip_tracking.py:98-109: `tree.map(lambda x: x[info["clip_idx"]], self._reference_clips)` -- the clip(s) the
+        given env(s) track.  A scalar `clip_idx` gives one clip `(clip_len, d)` (the call at wandb_logging.py:136), a vector gives
+        `(n, clip_len, d)` per field, like the reference under vmap.  Out-of-range indices clamp, as jnp indexing does.  Host arrays."""
+        idx = info["clip_idx"]
+        idx = idx.detach().cpu().numpy() if isinstance(idx, torch.Tensor) else np.asarray(idx)
+        idx = np.clip(idx.astype(np.int64), 0, self._n_clips - 1)
+        fields = {f.name: getattr(self._reference_clips, f.name) for f in dataclasses.fields(self._reference_clips)}
+        return type(self._reference_clips)(**{k: (None if v is None else np.asarray(v)[idx]) for k, v in fields.items()})
+
+    def _get_cur_frame(self, info, data) -> torch.Tensor:
+        """reference single_clip_tracking.py:452-454 (fp32 multiply, add, floor): same arithmetic as the kernel's frame index."""
+        t = torch.as_tensor(data.time, dtype=torch.float32, device=self.device)
+        return torch.floor(t * torch.tensor(float(self._mocap_hz), dtype=torch.float32, device=self.device)
+                           + info["start_frame"].to(torch.float32)).to(torch.int32)
+
+    def _get_obs(self, data, info):
+        """reference single_clip_tracking.py:394-450 -> (reference_obs, proprioceptive_obs).  The observation is produced inside the step /
+        forward launch; this accessor serves it for the env's LIVE state (the only state for which it exists on the device) and refuses
+        a foreign `data` instead of returning a stale observation."""
+        live = self.stepper.buf["qpos"]
+        q = getattr(data, "qpos", None)
+        if not (isinstance(q, torch.Tensor) and q.data_ptr() == live.data_ptr()):
+            raise ValueError("_get_obs serves the env's live pipeline_state only: step / reset_from_clip compute the observation in the same "
+                             "launch as the physics; put the state into the env (reset_from_clip) to observe it")
+        r = self.stepper.dims["reference_obs_size"]
+        obs = self.stepper.buf["obs"]
+        return obs[:, :r], obs[:, r:]
+
+
+class ReferenceFrameView:
+    """`info["reference_frame"]` (single_clip_tracking.py:223-226: `tree.map(lambda x: x[cur_frame], reference_clip)`) without
+    materialising 616 floats per env per step: each ReferenceClip field is gathered from the device clip table when it is read
+    (`state.info["reference_frame"].position`, as wrappers.py:353-363 does).  Index clamping follows jnp."""
+
+    FIELDS = ("position", "quaternion", "joints", "body_positions", "velocity", "angular_velocity", "joints_velocity", "body_quaternions")
+
+    def __init__(self, env: "MultiClipTracking", clip_idx: torch.Tensor, cur_frame: torch.Tensor):
+        self._env, self._clip, self._frame = env, clip_idx, cur_frame
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in self.FIELDS:
+            raise AttributeError(name)
+        tab = self._env._clip_field(name)
+        ci = self._clip.long().clamp(0, tab.shape[0] - 1)
+        fr = self._frame.long().clamp(0, tab.shape[1] - 1)
+        return tab[ci, fr]
 
 
 def wrap(env: MultiClipTracking, episode_length: int | None = None) -> MultiClipTracking:
@@ -279,8 +350,14 @@ def wrap(env: MultiClipTracking, episode_length: int | None = None) -> MultiClip
     The env is already batched, and the episode counter / truncation / `where(done, first_*, cur)` restore are
     executed inside the step launch (TMJX_F_AUTORESET), so this only switches the fused path on.
     """
-    if episode_length is not None and int(episode_length) != env.cfg.episode_length:
-        env.cfg.episode_length = int(episode_length)
-        raise ValueError("episode_length is fixed at construction (clip_length - random_init_range - traj_length)")
+    if episode_length is not None:
+        import math
+
+        limit = int(math.ceil(float(episode_length) - 1e-9))     # brax: `steps >= episode_length` on an integer-valued counter
+        if limit <= 0:
+            raise ValueError("episode_length must be positive")
+        if limit != env.cfg.episode_length:
+            env.stepper.set_episode_length(limit)            # pushed to the device model; nothing is changed when this raises
+            env.cfg.episode_length = limit
     env._autoreset = True
     return env

@@ -44,15 +44,21 @@ class Shard:
         return int(base_seed) * 1000003 + self.rank
 
 
-def reduce_episode_stats(reward_sum: torch.Tensor, done_sum: torch.Tensor, n_steps: int, shard: Shard, group=None) -> dict:
-    """Whole-job mean reward / done fraction: SUM all-reduce of two scalars (the only env-path collective)."""
+def reduce_episode_stats(reward_sum: torch.Tensor, done_sum: torch.Tensor, n_steps: int, shard: Shard, group=None, nan_sum=None) -> dict:
+    """Whole-job mean reward / done fraction (/ NaN fraction): SUM all-reduce of a few scalars (the only env-path collective)."""
     import torch.distributed as dist
 
-    stats = torch.stack([reward_sum.double().reshape(()), done_sum.double().reshape(())])
+    parts = [reward_sum.double().reshape(()), done_sum.double().reshape(())]
+    if nan_sum is not None:
+        parts.append(nan_sum.double().reshape(()))
+    stats = torch.stack(parts)
     if shard.world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     denom = float(shard.global_envs * n_steps)
-    return {"mean_reward": float(stats[0].item()) / denom, "done_frac": float(stats[1].item()) / denom}
+    out = {"mean_reward": float(stats[0].item()) / denom, "done_frac": float(stats[1].item()) / denom}
+    if nan_sum is not None:
+        out["nan_frac"] = float(stats[2].item()) / denom
+    return out
 
 
 def max_over_ranks(value: float, device, shard: Shard, group=None) -> float:
