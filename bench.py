@@ -419,6 +419,13 @@ def run_ppo(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     max_ms = max_over_ranks(dev_ms, dev, shard)
     ppo.timing = False
+    # data-parallel invariant: every rank holds the same parameters after the same number of updates (pmean'd gradients, same seeds)
+    params_identical = None
+    if world > 1:
+        cs = torch.stack([ppo.trainer.params.double().sum(), ppo.trainer.params.double().abs().sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        params_identical = bool(torch.equal(lo, hi))
     # the same steps with the gradient all-reduce switched off: the difference is what the collective costs when it is NOT hidden
     exposed_ms = None
     if world > 1:
@@ -457,7 +464,8 @@ def run_ppo(args, rank, world, local_rank):
                     "gemm_tflops_tf32": flops_mb * n_mb / (phases.get("sgd", 1e-9) / K * 1e-3) / 1e12,
                     "gradient_bytes": int(ppo.trainer.n_params) * 4,
                     "allreduce_exposed_ms_per_step": exposed_ms,
-                    "allreduce_share_of_step": None if exposed_ms is None else exposed_ms / (max_ms / K)},
+                    "allreduce_share_of_step": None if exposed_ms is None else exposed_ms / (max_ms / K),
+                    "params_identical_across_ranks": params_identical},
         "gpu_launches": None, "wall_s_timed_region": wall, "losses_last_minibatch": [float(x) for x in losses.cpu()],
     }
     emit(out)

@@ -7,10 +7,12 @@
   * every step of the task-layer golden vectors computed by the reference's own code, at the oracle's tolerance.
 
 Tolerance model: the reference is fp32 and the shipped CG 5/5 solve is an unconverged iterate, so a control step
-amplifies rounding by 1e2..1e5 depending on the env (contact-rich ones most).  The fp32 and fp64 oracles differ from each other by
-that noise; the kernel is held to the SAME distribution: percentiles of |cuda - fp32 oracle| must be within 2 x those of
-|fp32 oracle - fp64 oracle| (plus a floor of a few ulp of the state's scale), and `done` / frame indices must be bit-exact on
-every env on which the two oracles agree with each other.
+amplifies rounding by 1e2..1e5 depending on the env (contact-rich ones most) and a free run separates chaotically once contacts engage:
+the fp32 and fp64 oracles -- the same algorithm -- are 0.1 rad apart after 10 control steps at action scale 0.01
+(profiles/r2b_parity_horizon_table.txt).  The kernel is held to the SAME distribution at every step: percentiles of |cuda - fp64 oracle|
+within 2 x those of |fp32 oracle - fp64 oracle|, of |cuda - fp32 oracle| within 3 x (two independent rounding sequences), plus a floor
+of a few ulp of the state's scale; frame / ring-buffer indices bit-exact always; `done` bit-exact on every env whose termination
+margins exceed 100 x its own state error, and no more `done` flips against the fp32 oracle than that oracle has against fp64.
 """
 import json
 import os

@@ -69,3 +69,46 @@ def test_shard_partition_properties():
             assert sum(s.count for s in shards) == n
             assert all(shards[i].stop == shards[i + 1].start for i in range(w - 1))
             assert max(s.count for s in shards) - min(s.count for s in shards) <= 1
+
+
+def _bucket_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from track_mjx_b200.sharding import GradientBuckets
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)        # rank r holds (r + 1) x [0..9]
+    b = GradientBuckets(g, [4])
+    b.reduce(1)                                                   # the later part of the buffer first, as the backward pass produces it
+    g[:4] += 100.0                                                # "policy backward" still writing bucket 0 while bucket 1 is in flight
+    b.reduce(0)
+    scale = b.wait()
+    out.put((rank, g.tolist(), scale, len(b)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_is_the_pmean():
+    """The N > 1 learner path (BASELINE configs[3]): SUM all-reduce per bucket + 1 / world_size scale = jax.lax.pmean of the gradients."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    base = torch.arange(10, dtype=torch.float32)
+    want = (base * 3).tolist()                                    # (1 + 2) x [0..9]
+    want[:4] = [v + 200.0 for v in want[:4]]
+    for rank, got, scale, nb in res:
+        assert got == want and scale == 0.5 and nb == 2
+    import pytest
+
+    from track_mjx_b200.sharding import GradientBuckets
+    with pytest.raises(ValueError):
+        GradientBuckets(torch.zeros(8), [9])
+    assert GradientBuckets(torch.zeros(8), [3]).wait() == 1.0     # no process group: identity, scale 1

@@ -77,27 +77,33 @@ def build_solve_ir(t: Tree):
     nslot = (nv + 31) // 32
     ir = []
     by_level = [[i for i in range(nv) if t.depth[i] == lv] for lv in range(t.maxdepth + 1)]
+    # Pivots of one tree level are independent of each other (none is an ancestor of another), so a level first broadcasts ALL of
+    # its pivot values (independent shuffles, issued back to back: one shuffle latency per level instead of one per pivot -- with a
+    # single pivot register every shuffle had to wait for the predicated FFMA that last wrote its source register, a false
+    # dependency) and then applies the updates.  The critical path is the deepest chain (36 levels), not the 73 pivots.
     # ---- x <- L^-T x: pivot i (deepest level first) updates its ancestors: x[j] -= L[i][j] x[i]
     for lv in range(t.maxdepth, 0, -1):
-        for i in sorted(by_level[lv], reverse=True):
-            ir.append(("shfl", "p", f"x{i // 32}", i % 32))
+        piv = sorted(by_level[lv], reverse=True)
+        for k, i in enumerate(piv):
+            ir.append(("shfl", f"p{k}", f"x{i // 32}", i % 32))
+        for k, i in enumerate(piv):
             for s in range(nslot):
                 m = lane_mask(t.anc[i], s)
                 if m:
-                    ir.append(("fnma_lds", f"x{s}", f"U{s}", t.rowend[i], "p", m))
+                    ir.append(("fnma_lds", f"x{s}", f"U{s}", t.rowend[i], f"p{k}", m))
     # ---- x <- D^-1 x (the factorisation leaves 1/D on the diagonal)
     for s in range(nslot):
         ir.append(("mul_lds", f"x{s}", f"G{s}", 0, lane_mask(range(nv), s)))
     # ---- x <- L^-1 x: pivot j (root first) updates its descendants: x[i] -= L[i][j] x[j]
     for lv in range(0, t.maxdepth):
-        for j in by_level[lv]:
-            if not t.desc[j]:
-                continue
-            ir.append(("shfl", "p", f"x{j // 32}", j % 32))
+        piv = [j for j in by_level[lv] if t.desc[j]]
+        for k, j in enumerate(piv):
+            ir.append(("shfl", f"p{k}", f"x{j // 32}", j % 32))
+        for k, j in enumerate(piv):
             for s in range(nslot):
                 m = lane_mask(t.desc[j], s)
                 if m:
-                    ir.append(("fnma_lds", f"x{s}", f"D{s}", -t.depth[j], "p", m))
+                    ir.append(("fnma_lds", f"x{s}", f"D{s}", -t.depth[j], f"p{k}", m))
     return ir
 
 
@@ -132,6 +138,9 @@ def chains_descending(t: Tree):
     return out
 
 
+K_BATCH = 6      # pivot-row broadcasts in flight per batch of the factorisation
+
+
 def build_factor_ir(t: Tree):
     """Chain-at-a-time elimination: the rows a chain's pivots touch (the chain itself + the ancestors of its top end) are
     loaded into registers once, every pivot of the chain then updates them with shuffle + FMA only, and they are stored
@@ -162,14 +171,21 @@ def build_factor_ir(t: Tree):
             jd = c >> 4
             ir.append(("st", re - 16 * jd, "inv", half_mask((c & 15) + 1) & ~half_mask(c & 15)))
             chain = [k] + t.anc[k]                    # chain[a] = a-th ancestor, depth c - a
-            for al in range(c - 1, -1, -1):
-                row = chain[c - al]
-                ir.append(("shflh", "a", f"r{k}_{al >> 4}", al & 15))
-                for j in range(al // 16 + 1):
-                    # UNMASKED: lanes beyond the row's last column (i > al - 16 j) get polluted, but a lane's entry is only
-                    # ever combined with the same lane of other rows, shuffles read lanes <= depth and stores are masked,
-                    # so the pollution never reaches a valid entry (run_factor_ir executes it on all 32 lanes, too)
-                    ir.append(("fnma_reg", f"r{row}_{j}", "a", f"w{j}", 0xFFFFFFFF))
+            # the pivot-row broadcasts of a pivot are independent of each other (they read the finished row k): emit them in
+            # batches of kBatch BEFORE the row updates that consume them, so that an in-order warp pays one shuffle latency per
+            # batch instead of one per ancestor row (measured: the factorisation was 1046 exposed shuffle latencies)
+            als = list(range(c - 1, -1, -1))
+            for b0 in range(0, len(als), K_BATCH):
+                batch = als[b0:b0 + K_BATCH]
+                for q, al in enumerate(batch):
+                    ir.append(("shflh", f"a{q}", f"r{k}_{al >> 4}", al & 15))
+                for q, al in enumerate(batch):
+                    row = chain[c - al]
+                    for j in range(al // 16 + 1):
+                        # UNMASKED: lanes beyond the row's last column (i > al - 16 j) get polluted, but a lane's entry is only
+                        # ever combined with the same lane of other rows, shuffles read lanes <= depth and stores are masked,
+                        # so the pollution never reaches a valid entry (run_factor_ir executes it on all 32 lanes, too)
+                        ir.append(("fnma_reg", f"r{row}_{j}", f"a{q}", f"w{j}", 0xFFFFFFFF))
         for r in t.anc[bottom]:                       # ancestors of the chain: updated, not yet eliminated
             for j in range(t.depth[r] // 16 + 1):
                 ir.append(("st", t.rowend[r] - 16 * j, f"r{r}_{j}", half_mask(t.depth[r] - 16 * j + 1)))
@@ -221,17 +237,19 @@ def build_mulm_ir(t: Tree):
     ir = []
     for s in range(nslot):
         ir.append(("mulset_lds", f"y{s}", f"x{s}", f"G{s}", 0, lane_mask(range(t.nv), s)))
-    for p in range(t.nv):
-        if not t.desc[p] and not t.anc[p]:
-            continue
-        ir.append(("shfl", "p", f"x{p // 32}", p % 32))
-        for s in range(nslot):
-            m = lane_mask(t.desc[p], s)
-            if m:
-                ir.append(("fma_lds", f"y{s}", f"D{s}", -t.depth[p], "p", m))
-            m = lane_mask(t.anc[p], s)
-            if m:
-                ir.append(("fma_lds", f"y{s}", f"U{s}", t.rowend[p], "p", m))
+    piv = [p for p in range(t.nv) if t.desc[p] or t.anc[p]]
+    for b0 in range(0, len(piv), K_BATCH):          # x is read-only: the broadcasts of a batch are independent, issue them first
+        batch = piv[b0:b0 + K_BATCH]
+        for q, p in enumerate(batch):
+            ir.append(("shfl", f"p{q}", f"x{p // 32}", p % 32))
+        for q, p in enumerate(batch):
+            for s in range(nslot):
+                m = lane_mask(t.desc[p], s)
+                if m:
+                    ir.append(("fma_lds", f"y{s}", f"D{s}", -t.depth[p], f"p{q}", m))
+                m = lane_mask(t.anc[p], s)
+                if m:
+                    ir.append(("fma_lds", f"y{s}", f"U{s}", t.rowend[p], f"p{q}", m))
     return ir
 
 
@@ -392,7 +410,9 @@ def emit_cuda(t: Tree) -> str:
     w("// x <- (L^T D L)^-1 x.  L: this env's sparse factor in shared memory (diagonal holds 1/D);")
     w("// dep* / rend* : depth and row-end of the dofs this lane owns (lane, lane+32, lane+64).")
     w("static __device__ __noinline__ V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
-    w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c, p, np;")
+    npiv = 1 + max(int(op[1][1:]) for op in ir if op[0] == "shfl")
+    w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c;")
+    w("  float " + ", ".join(f"p{k}, np{k}" for k in range(npiv)) + ";")
     w("  const unsigned lb = 1u << lane;")
     w("  const unsigned sL = static_cast<unsigned>(__cvta_generic_to_shared(L));")
     for s in range(3):
@@ -402,10 +422,10 @@ def emit_cuda(t: Tree) -> str:
     full = 0xFFFFFFFF
     for op in ir:
         if op[0] == "shfl":
-            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]}); np = -p;")
+            w(f"  {op[1]} = __shfl_sync(0xffffffffu, {op[2]}, {op[3]}); n{op[1]} = -{op[1]};")
         elif op[0] == "fnma_lds":
             _, xr, ptr, imm, p, mask = op
-            w(_pred_fma(xr, ptr, imm, "p", mask, True))
+            w(_pred_fma(xr, ptr, imm, p, mask, True))
         elif op[0] == "mul_lds":
             _, xr, ptr, imm, mask = op
             guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
@@ -416,7 +436,7 @@ def emit_cuda(t: Tree) -> str:
     w("// y = M x with the raw sparse inertia at M (before it is factored); x, y: dof-lane registers.")
     w("static __device__ __noinline__ V3 mul_m(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
     w("  const float x0 = xin.a, x1 = xin.b, x2 = xin.c;")
-    w("  float y0 = 0.f, y1 = 0.f, y2 = 0.f, p;")
+    w("  float y0 = 0.f, y1 = 0.f, y2 = 0.f, " + ", ".join(f"p{q}" for q in range(K_BATCH)) + ";")
     w("  const unsigned lb = 1u << lane;")
     w("  const unsigned sL = static_cast<unsigned>(__cvta_generic_to_shared(L));")
     for s in range(3):
@@ -425,14 +445,14 @@ def emit_cuda(t: Tree) -> str:
         w(f"  const float* G{s} = L + (rend{s} - dep{s});")
     for op in build_mulm_ir(t):
         if op[0] == "shfl":
-            w(f"  p = __shfl_sync(0xffffffffu, {op[2]}, {op[3]});")
+            w(f"  {op[1]} = __shfl_sync(0xffffffffu, {op[2]}, {op[3]});")
         elif op[0] == "mulset_lds":
             _, yr, xr, ptr, imm, mask = op
             guard = "" if mask == full else f"if (lb & 0x{mask:08x}u) "
             w(f"  {guard}{yr} = {xr} * {ptr}[{imm}];")
         elif op[0] == "fma_lds":
             _, yr, ptr, imm, p, mask = op
-            w(_pred_fma(yr, ptr, imm, "p", mask, False))
+            w(_pred_fma(yr, ptr, imm, p, mask, False))
     w("  V3 r; r.a = y0; r.b = y1; r.c = y2;")
     w("  return r;")
     w("}")
@@ -445,7 +465,7 @@ def emit_cuda(t: Tree) -> str:
     w("  const int hbit = lane & 16;")
     w("  float* ps = L + (hbit ? off2 : 0) - (lane & 15);")
     fir = build_factor_ir(t)
-    w("  float w0 = 0.f, w1 = 0.f, w2 = 0.f, d, inv, a;")
+    w("  float w0 = 0.f, w1 = 0.f, w2 = 0.f, d, inv, " + ", ".join(f"a{q}" for q in range(K_BATCH)) + ";")
     declared = set()
     for op in fir:
         if op[0] == "sync":

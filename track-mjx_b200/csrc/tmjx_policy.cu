@@ -814,6 +814,22 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
 }
 
 constexpr int kPpoMaxPerLane = 8;   // action elements per lane of a row group: A <= 64
+// kFast: MUFU-based exp / log / tanh (ex2.approx / lg2.approx, ~2 ulp; absolute error of a row's log-prob ~1e-6): the row kernel is
+// issue-bound on the accurate libm chains (three softplus, a log, a tanh per action element), not on memory.  The reference's
+// jnp.exp / log on GPU are XLA's own polynomial approximations of comparable accuracy.  TMJX_PPO_ACCURATE=1 selects libm.
+template <bool kFast> __device__ __forceinline__ float exp_t(float x) { return kFast ? __expf(x) : expf(x); }
+template <bool kFast> __device__ __forceinline__ float log_t(float x) { return kFast ? __logf(x) : logf(x); }
+template <bool kFast> __device__ __forceinline__ float softplus_t(float x) {
+  return kFast ? fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))) : softplus(x);
+}
+template <bool kFast> __device__ __forceinline__ float tanh_t(float x) {
+  if (!kFast) return tanhf(x);
+  const float e = __expf(-2.f * fabsf(x));                  // in (0, 1]: no overflow
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+template <bool kFast> __device__ __forceinline__ float log_det_tanh_t(float x) { return 2.f * (0.69314718055994531f - x - softplus_t<kFast>(-2.f * x)); }
+
+template <bool kFast>
 __global__ void __launch_bounds__(32 * kPpoWarps) ppo_fused_kernel(const float* __restrict__ logits, const float* __restrict__ raw_action,
                                                         const float* __restrict__ eps, const float* __restrict__ lat_mean,
                                                         const float* __restrict__ lat_logvar, const float* __restrict__ baseline,
@@ -841,16 +857,16 @@ __global__ void __launch_bounds__(32 * kPpoWarps) ppo_fused_kernel(const float* 
       for (int q = 0; q < kPpoMaxPerLane; ++q) {
         const int i = lane + q * kPpoLanes;
         if (i < A) {
-          const float loc = lg[i], sr = lg[A + i], scale = softplus(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
-          const float z = (raw - loc) / scale, ls = logf(scale), x = fmaf(scale, e, loc);
-          lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh(raw);
-          en += 0.5f + 0.91893853320467274f + ls + log_det_tanh(x);
-          r_z[q] = z; r_rs[q] = 1.f / scale; r_dj[q] = -2.f * tanhf(x); r_sig[q] = 1.f / (1.f + expf(-sr)); r_e[q] = e;
+          const float loc = lg[i], sr = lg[A + i], scale = softplus_t<kFast>(sr) + 0.001f, raw = raw_action[row * A + i], e = eps[row * A + i];
+          const float z = (raw - loc) / scale, ls = log_t<kFast>(scale), x = fmaf(scale, e, loc);
+          lp += -0.5f * z * z - ls - 0.91893853320467274f - log_det_tanh_t<kFast>(raw);
+          en += 0.5f + 0.91893853320467274f + ls + log_det_tanh_t<kFast>(x);
+          r_z[q] = z; r_rs[q] = 1.f / scale; r_dj[q] = -2.f * tanh_t<kFast>(x); r_sig[q] = __fdividef(1.f, 1.f + exp_t<kFast>(-sr)); r_e[q] = e;
         }
       }
       const float *mu = lat_mean + row * L, *lv = lat_logvar + row * L, *mp = mu - size_t(B) * L, *mn = mu + size_t(B) * L;
       for (int j = lane; j < L; j += kPpoLanes) {
-        const float m = mu[j], v = lv[j], ev = expf(v);
+        const float m = mu[j], v = lv[j], ev = exp_t<kFast>(v);
         float gm, gv;
         if (t == 0) {
           k += 1.f + v - m * m - ev;
@@ -867,7 +883,7 @@ __global__ void __launch_bounds__(32 * kPpoWarps) ppo_fused_kernel(const float* 
     }
     lp = group_sum(lp); en = group_sum(en); k = group_sum(k);
     if (!live) continue;
-    const float a = (adv_raw[row] - adv_mean) * adv_inv, rho = expf(lp - behaviour_logp[row]);
+    const float a = (adv_raw[row] - adv_mean) * adv_inv, rho = exp_t<kFast>(lp - behaviour_logp[row]);
     const float clipped = fminf(fmaxf(rho, 1.f - hp.clipping_epsilon), 1.f + hp.clipping_epsilon);
     const float s1 = rho * a, s2 = clipped * a;
     const float cp = (s1 <= s2) ? -a * rho * inv_n : 0.f;
@@ -1494,9 +1510,15 @@ int tmjx_ppo_loss_head(const float* logits, const float* latent_mean, const floa
     const int nb0 = int(std::min<size_t>(kPpoBlocks, (n + 255) / 256));
     adv_stats_kernel<<<nb0, 256, 0, st>>>(adv_raw, n, partial);
     ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nb0, 0, T, B, L, hp, losses);
-    ppo_fused_kernel<<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, behaviour_log_prob,
-                                                       losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean, d_latent_logvar,
-                                                       d_baseline, partial);
+    static const bool accurate = [] { const char* e = std::getenv("TMJX_PPO_ACCURATE"); return e && atoi(e); }();
+    if (accurate)
+      ppo_fused_kernel<false><<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, behaviour_log_prob,
+                                                                losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean, d_latent_logvar,
+                                                                d_baseline, partial);
+    else
+      ppo_fused_kernel<true><<<nblk, 32 * kPpoWarps, 0, st>>>(logits, raw_action, eps_entropy, latent_mean, latent_logvar, baseline, vs, behaviour_log_prob,
+                                                               losses, T, B, A, L, hp, adv_raw, advantages, d_logits, d_latent_mean, d_latent_logvar,
+                                                               d_baseline, partial);
     ppo_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, 3, T, B, L, hp, losses);
     PCU(cudaGetLastError());
     return TMJX_OK;

@@ -45,6 +45,7 @@ struct KArgs {
   int n_env;
   unsigned flags;
   float* spill;   // per resident warp: m.spill_floats floats (compact CG layout), else unused
+  int phase_offset_ns;   // two-blocks-per-SM variant: the upper half of the grid starts this much later (complementary phases)
 };
 
 #ifdef TMJX_VARIANT  // device code: compiled once per residency variant, in parallel (see __graft_entry__.build)
@@ -1356,7 +1357,7 @@ __device__ void solve_cg(const Warp& w, const Rows& r, const float qfs[kNvSlots]
   const float* L1 = w.at(m.o_L);
   // the residency variants are solver-specialised: 14 warps = CG only, 10 warps = Newton only (its slice carries a third
   // matrix), 4 warps = either (runtime); dropping the other solver's code shrinks the hot kernel's instruction footprint
-#if TMJX_VARIANT >= 14
+#if TMJX_VARIANT >= 14 || TMJX_VARIANT == 7
   constexpr bool newton = false;
 #elif TMJX_VARIANT == 10
   constexpr bool newton = true;
@@ -1763,6 +1764,12 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
   // of rounds is block-uniform; a warp without an environment in the last round recomputes the block's last one
   // (reads only, nothing is written) so that it keeps arriving at the phase barriers.
   const int G = gridDim.x, count = (a.n_env - int(blockIdx.x) + G - 1) / G, nrounds = (count + wpb - 1) / wpb;
+  if (a.phase_offset_ns > 0 && int(blockIdx.x) >= (G + 1) / 2) {
+    // the second block of an SM runs half a substep behind the first: the two blocks then sit in different phases (tree passes /
+    // factorisation vs solver) and compete less for the shuffle / shared-memory pipe than 14 warps in one phase
+    const long long t0 = clock64(), wait = (long long)(a.phase_offset_ns) * 2;   // ~2 cycles per ns
+    while (clock64() - t0 < wait) __nanosleep(1000);
+  }
   for (int rd = 0; rd < nrounds; ++rd) {
     const int slot = rd * wpb + warp;
     const bool live = slot < count;
@@ -2032,6 +2039,9 @@ __global__ void __launch_bounds__(kWPB * 32, kMinBlocks) tmjx_env_kernel(const _
 #if TMJX_VARIANT >= 14
 #define TMJX_WPB TMJX_VARIANT
 #define TMJX_MINB 1
+#elif TMJX_VARIANT == 7
+#define TMJX_WPB 7
+#define TMJX_MINB 2
 #elif TMJX_VARIANT == 10
 #define TMJX_WPB 10
 #define TMJX_MINB 1
@@ -2076,6 +2086,11 @@ TMJX_DECL_VARIANT(14)
 #else
 TMJX_STUB_VARIANT(14)
 #endif
+#ifdef TMJX_HAVE_VARIANT_7
+TMJX_DECL_VARIANT(7)
+#else
+TMJX_STUB_VARIANT(7)
+#endif
 #ifdef TMJX_HAVE_VARIANT_16
 TMJX_DECL_VARIANT(16)
 #else
@@ -2119,6 +2134,7 @@ struct TmjxModel {
   int device = 0, sm_count = 0, envs_per_block = 12, max_blocks_per_sm = 1;
   int envs_per_block_alt = 0;   // CG: the 16-warp residency variant, taken when it saves a lock-step round for the batch at hand
   int force_epb = 0;            // TMJX_ENVS_PER_BLOCK
+  int phase_offset_ns = 0;      // TMJX_PHASE_OFFSET_US (7-warp x 2-block variant)
   size_t smem_per_env = 0;
   float* d_spill = nullptr;     // [sm_count * max_blocks_per_sm * max envs per block, spill_floats] (compact CG layout)
   TmjxTaskConfig cfg;
@@ -2191,7 +2207,9 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
     if (v == 4) { m->envs_per_block = 4; m->envs_per_block_alt = 0; }
     if (v == 14 && m->envs_per_block == 14) m->envs_per_block_alt = 0;
     if (v == 16 && m->envs_per_block == 14 && per_env * 16 <= optin) { m->envs_per_block = 16; m->envs_per_block_alt = 0; }
+    if (v == 7 && m->envs_per_block == 14) { m->envs_per_block = 7; m->envs_per_block_alt = 0; }
   }
+  if (const char* e = std::getenv("TMJX_PHASE_OFFSET_US")) m->phase_offset_ns = atoi(e) * 1000;   // tuning knob
   if (const char* e = std::getenv("TMJX_NO_GEN")) { if (atoi(e)) m->dm.use_gen = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_SEG")) { if (atoi(e)) m->dm.use_seg = 0; }                    // tuning knob
   if (const char* e = std::getenv("TMJX_NO_DSC4")) { if (atoi(e)) m->dm.use_dsc4 = 0; }                  // tuning knob
@@ -2204,11 +2222,11 @@ int tmjx_model_create(const void* blob, size_t nbytes, const TmjxTaskConfig* cfg
   m->dm.sync_every = 1;
   if (const char* e = std::getenv("TMJX_SYNC_EVERY")) m->dm.sync_every = std::max(1, atoi(e));           // tuning knob
   if (per_env * m->envs_per_block > optin) return fail(TMJX_E_UNSUPPORTED, "model does not fit in shared memory (unsupported)");
-  m->max_blocks_per_sm = m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (per_env * 4 + 1024)));
+  m->max_blocks_per_sm = m->envs_per_block == 7 ? 2 : (m->envs_per_block != 4 ? 1 : int(std::max<size_t>(1, prop.sharedMemPerMultiprocessor / (per_env * 4 + 1024))));
   for (int epb : {m->envs_per_block, m->envs_per_block_alt}) {
     if (!epb) continue;
     const int dyn = int(per_env * epb);
-    CU(epb == 16 ? variant_attr_16(dyn) : (epb == 14 ? variant_attr_14(dyn) : (epb == 10 ? variant_attr_10(dyn) : variant_attr_4(dyn))));
+    CU(epb == 16 ? variant_attr_16(dyn) : (epb == 14 ? variant_attr_14(dyn) : (epb == 10 ? variant_attr_10(dyn) : (epb == 7 ? variant_attr_7(dyn) : variant_attr_4(dyn)))));
   }
   {
     const size_t slots = size_t(m->sm_count) * m->max_blocks_per_sm * std::max(m->envs_per_block, m->envs_per_block_alt);
@@ -2308,6 +2326,7 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   a.m = m->dm; a.task = m->d_task; a.clips = c->d_table; a.n_clips = c->n_clips; a.clip_len = c->clip_len;
   a.st = *s; a.out = *o; a.action = action; a.n_env = n_env; a.flags = flags;
   a.spill = m->d_spill;
+  a.phase_offset_ns = m->envs_per_block == 7 ? m->phase_offset_ns : 0;
   // residency variant: the block runs ceil(envs of the block / envs per block) lock-step rounds of the same duration whatever the
   // number of warps, so the wider block is taken exactly when it saves a round (4096 envs on 148 SMs: 28 per SM = 2 rounds either
   // way -> 14 warps and the larger L1; 16384: 111 per SM = 8 rounds of 14 or 7 of 16)
@@ -2322,7 +2341,8 @@ static int launch(const TmjxModel* m, const TmjxClips* c, const float* action, T
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(epb == 16 ? variant_launch_16(kStep, a, grid, smem, st)
                : (epb == 14 ? variant_launch_14(kStep, a, grid, smem, st)
-                            : (epb == 10 ? variant_launch_10(kStep, a, grid, smem, st) : variant_launch_4(kStep, a, grid, smem, st))));
+                            : (epb == 10 ? variant_launch_10(kStep, a, grid, smem, st)
+                                         : (epb == 7 ? variant_launch_7(kStep, a, grid, smem, st) : variant_launch_4(kStep, a, grid, smem, st)))));
   return TMJX_OK;
 }
 

@@ -235,3 +235,29 @@ class ValueNetwork:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------- golden cases
+# Seeded inputs of tests/golden/policy.npz (outputs computed by the reference's own module text, tools/make_golden_policy.py).
+GOLDEN_CASES = (
+    ("shipped", IntentionNetworkConfig(), 11, 48),                                                    # rodent-full-clips.yaml:50-57
+    ("small", IntentionNetworkConfig(obs_size=100, reference_obs_size=60, action_size=6, latent_size=12, encoder_layers=(96, 64),
+                                     decoder_layers=(64, 32)), 12, 40),
+)
+
+
+def golden_case(cfg: IntentionNetworkConfig, seed: int, rows: int):
+    """(params, obs [rows, obs_size], eps_latent [rows, latent]) regenerated from a seed (numpy PCG64: stable across versions).  The
+    parameters are random-init kernels with NON-trivial biases, LayerNorm scale / bias and normaliser, so that every term is exercised."""
+    rng = np.random.default_rng(seed)
+    p = init_params(cfg, seed)
+    for k in sorted(p):
+        if k.endswith("/bias"):
+            p[k] = (0.1 * rng.normal(size=p[k].shape)).astype(np.float32)
+        if k.endswith("/scale"):
+            p[k] = (1.0 + 0.2 * rng.normal(size=p[k].shape)).astype(np.float32)
+    p["norm/mean"] = (0.3 * rng.normal(size=cfg.obs_size)).astype(np.float32)
+    p["norm/std"] = (0.5 + rng.uniform(size=cfg.obs_size)).astype(np.float32)
+    obs = rng.normal(size=(rows, cfg.obs_size)).astype(np.float32)
+    eps = rng.normal(size=(rows, cfg.latent_size)).astype(np.float32)
+    return p, obs, eps

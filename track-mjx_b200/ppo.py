@@ -72,6 +72,9 @@ class PPO:
         self.perm_gen.manual_seed(c.seed + 17)
         self.it = 0
         self.state = None
+        from .sharding import GradientBuckets
+
+        self.buckets = GradientBuckets(self.trainer.grads, [self.trainer.n_policy])     # bucket 0 = policy vector, 1 = value vector
         self.timing, self.marks = False, []
         self.all_reduce = self.world > 1
 
@@ -105,18 +108,15 @@ class PPO:
                                mb["reward"], mb["discount"], mb["truncation"], mb["raw_action"], mb["log_prob"], eps_e,
                                entropy_cost=c.entropy_cost, kl_weight=kl_w, discounting=c.discounting, reward_scaling=c.reward_scaling,
                                gae_lambda=c.gae_lambda, clipping_epsilon=c.clipping_epsilon, normalize_advantage=c.normalize_advantage)
-        npol = tr.n_policy
         tr.value_backward(out["d_baseline"].reshape(rows))
-        work = []
         if self.all_reduce:
-            # value-network bucket: its all-reduce runs on NCCL's stream while the policy backward below keeps the SMs busy
-            work.append(torch.distributed.all_reduce(tr.grads[npol:], async_op=True))
+            self.buckets.reduce(1)    # value-network bucket: its all-reduce runs on NCCL's stream while the policy backward keeps the SMs busy
         tr.policy_backward(out["d_logits"].view(rows, 2 * A), out["d_latent_mean"].view(rows, Lz), out["d_latent_logvar"].view(rows, Lz))
+        scale = 1.0
         if self.all_reduce:
-            work.append(torch.distributed.all_reduce(tr.grads[:npol], async_op=True))
-            for w in work:
-                w.wait()                                                                          # the compute stream waits, the host does not
-        self.adam.step(tr.grads, all_reduce=False, grad_scale=1.0 / self.world)      # pmean = SUM (done above, bucket by bucket) / world_size
+            self.buckets.reduce(0)
+            scale = self.buckets.wait()                                            # the compute stream waits, the host does not
+        self.adam.step(tr.grads, all_reduce=False, grad_scale=scale)                # pmean = SUM (bucket by bucket) / world_size
         tr.sync()
         return out["losses"]
 

@@ -69,3 +69,38 @@ def max_over_ranks(value: float, device, shard: Shard, group=None) -> float:
     if shard.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class GradientBuckets:
+    """`jax.lax.pmean(grads, axis_name)` of the reference's `gradient_update_fn` (ppo.py:621-623, brax gradients.py) as bucketed SUM
+    all-reduces of ONE flat gradient tensor: a bucket is reduced as soon as the backward pass has produced it (`reduce(i)` right
+    after the kernels that write it were enqueued; the collective runs on the communicator's stream while later buckets are still
+    being computed), `wait()` makes the compute stream wait for all of them and returns the 1 / world_size scale the optimiser
+    applies (the buffer keeps the SUM).  Works on NCCL (CUDA tensors) and gloo (CPU tensors, tests/test_sharding_gloo.py)."""
+
+    def __init__(self, grads: torch.Tensor, boundaries, group=None):
+        if grads.dim() != 1 or not grads.is_contiguous():
+            raise ValueError("grads must be a flat contiguous tensor")
+        b = [0] + [int(x) for x in boundaries] + [grads.numel()]
+        if any(b[i] >= b[i + 1] for i in range(len(b) - 1)):
+            raise ValueError("bucket boundaries must be strictly increasing offsets inside the gradient buffer")
+        self.views = [grads[b[i]:b[i + 1]] for i in range(len(b) - 1)]
+        self.group, self._work = group, []
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def __len__(self):
+        return len(self.views)
+
+    def reduce(self, i: int):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            self._work.append(dist.all_reduce(self.views[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self) -> float:
+        for w in self._work:
+            w.wait()
+        self._work = []
+        return 1.0 / self.world
