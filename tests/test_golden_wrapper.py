@@ -1,0 +1,83 @@
+"""Fused episode / auto-reset semantics against golden vectors computed by the REFERENCE'S OWN `AutoResetWrapperTracking.step` text
+(tools/make_golden_wrapper.py cuts the class out of `track_mjx/environment/wrappers.py:277-310` and runs it around the restated brax
+`EpisodeWrapper` + the oracle's un-wrapped step).  CPU: the oracle's fused TMJX_F_AUTORESET path must reproduce the recorded outputs
+bit for bit (same fp32 physics underneath, so any difference is wrapper logic).  GPU: the kernel's fused path against the same file:
+wrapper state (`steps`, `truncation`, `done`) bit-exact, restored rows bit copies of the snapshot, the rest at the substep tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from oracle.oracle import Oracle
+from track_mjx_b200 import _lib as L
+from track_mjx_b200 import clips as clipmod, config
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wrapper.npz")
+PIPE = ("qpos", "qvel", "act", "time", "qacc_warmstart", "xpos", "xquat", "qfrc_actuator")
+INFO = ("clip_idx", "start_frame", "buffer_index", "prev_ctrl", "action_buffer", "steps", "truncation")
+
+
+def _cfg(walker, g):
+    args = {k: v for k, v in config.DEFAULT_ENV_ARGS.items() if k != "reset_noise_scale"}
+    args["physics_steps_per_control_step"] = int(g["n_frames"])
+    cfg = config.make_task_config(walker, config.RewardConfig(), **args)
+    cfg.episode_length = int(g["episode_length"])
+    return cfg
+
+
+def _load_step(buf, g, t):
+    vals = {k: g["in_" + k][t] for k in PIPE + INFO + ("obs", "done")}
+    vals.update({"first_" + k: g["first_" + k] for k in PIPE})
+    vals.update(first_obs=g["first_obs"], first_prev_ctrl=g["first_prev_ctrl"])
+    common.put(buf, vals)
+
+
+def test_oracle_fused_wrappers_reproduce_the_reference_wrapper(walker, clips2):
+    g = np.load(GOLD)
+    cfg = _cfg(walker, g)
+    T, n = g["action"].shape[:2]
+    o = Oracle(walker.blob, cfg, clips2, dtype=np.float32)
+    buf = o.alloc(n, debug=False)
+    kinds = set()
+    for t in range(T):
+        _load_step(buf, g, t)
+        o.step(buf, g["action"][t], L.TMJX_F_AUTORESET)
+        for k in PIPE + INFO + ("obs", "done"):
+            assert np.array_equal(buf[k], g["out_" + k][t].reshape(buf[k].shape), equal_nan=True), (t, k)
+        d, tr = g["out_done"][t].ravel() != 0, g["out_truncation"][t].ravel() != 0
+        kinds |= {"terminated"} if (d & ~tr).any() else set()
+        kinds |= {"truncated"} if tr.any() else set()
+        kinds |= {"running"} if (~d).any() else set()
+        # restored rows are the snapshot; un-restored info persists (wrappers.py:124-131 touches pipeline_state, obs, prev_ctrl only)
+        assert np.array_equal(g["out_qpos"][t][d], g["first_qpos"][d]) and np.array_equal(g["out_obs"][t][d], g["first_obs"][d])
+        assert np.array_equal(g["out_start_frame"][t], g["in_start_frame"][t])
+    assert kinds == {"terminated", "truncated", "running"}          # the recording covers all three outcomes
+
+
+@pytest.mark.gpu
+def test_cuda_fused_wrappers_match_the_reference_wrapper(walker, clips2):
+    import torch
+
+    from track_mjx_b200.env import Stepper
+
+    g = np.load(GOLD)
+    cfg = _cfg(walker, g)
+    T, n = g["action"].shape[:2]
+    s = Stepper(walker.blob, cfg, clips2, n, 0)
+    for t in range(T):
+        _load_step(s.buf, g, t)
+        s.step(torch.from_numpy(g["action"][t]).cuda(), L.TMJX_F_AUTORESET)
+        out = common.get(s.buf)
+        sane = np.isfinite(g["in_qvel"][t]).all(1) & (np.abs(g["in_qvel"][t]).max(1) < 1e3) & np.isfinite(g["out_qpos"][t]).all(1)
+        for k in ("steps", "truncation", "buffer_index", "start_frame", "clip_idx", "action_buffer"):
+            assert np.array_equal(out[k], g["out_" + k][t].reshape(out[k].shape)), (t, k)
+        assert np.array_equal(out["done"][sane], g["out_done"][t].reshape(out["done"].shape)[sane]), t
+        d = (out["done"][:, 0] != 0) & sane
+        for k in ("qpos", "qvel", "act", "time", "obs", "prev_ctrl"):          # restored rows: bit copies of the snapshot
+            assert np.array_equal(out[k][d], g["out_" + k][t].reshape(out[k].shape)[d]), (t, k)
+        run = (out["done"][:, 0] == 0) & sane
+        for k, tol in (("qpos", 1e-4), ("obs", 2e-3)):                          # running rows: 5 substeps of fp32 physics
+            if run.any():
+                assert np.abs(out[k][run] - g["out_" + k][t].reshape(out[k].shape)[run]).max() < tol * max(1.0, np.abs(g["out_" + k][t]).max()), (t, k)
+    s.close()
