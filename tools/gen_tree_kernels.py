@@ -400,6 +400,11 @@ def emit_cuda(t: Tree) -> str:
     w(f"// dof_parentid of the tree this file was generated for (signature {t.signature()})")
     w("constexpr short kDofParent[kNv] = {" + ", ".join(str(p) for p in t.parent) + "};")
     w("struct V3 { float a, b, c; };")
+    w("// the solve is called from four sites of a substep: as a call it costs ~24 caller-side register spills + reloads per call (the")
+    w("// solver keeps ~90 live values per lane); -DTMJX_GEN_SOLVE_INLINE=__forceinline__ trades 2 k instructions of code for them")
+    w("#ifndef TMJX_GEN_SOLVE_INLINE")
+    w("#define TMJX_GEN_SOLVE_INLINE __noinline__")
+    w("#endif")
     w("#ifdef __CUDACC__")
     w("// 1/d as MUFU.RCP + one Newton step (3 instructions, <= 1 ulp) instead of the IEEE division sequence with its")
     w("// slow-path call: 73 pivots per factorisation, every physics substep")
@@ -409,7 +414,7 @@ def emit_cuda(t: Tree) -> str:
     w("}")
     w("// x <- (L^T D L)^-1 x.  L: this env's sparse factor in shared memory (diagonal holds 1/D);")
     w("// dep* / rend* : depth and row-end of the dofs this lane owns (lane, lane+32, lane+64).")
-    w("static __device__ __noinline__ V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
+    w("static __device__ TMJX_GEN_SOLVE_INLINE V3 solve(const float* __restrict__ L, V3 xin, int lane, int dep0, int dep1, int dep2, int rend0, int rend1, int rend2) {")
     npiv = 1 + max(int(op[1][1:]) for op in ir if op[0] == "shfl")
     w("  float x0 = xin.a, x1 = xin.b, x2 = xin.c;")
     w("  float " + ", ".join(f"p{k}, np{k}" for k in range(npiv)) + ";")

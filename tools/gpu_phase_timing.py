@@ -1,7 +1,7 @@
 """Critical-path breakdown of one environment's control step: clock64() cycles per phase, measured by warp 0 of block 0 of the
-14-warp CG kernel in a development build (tools/build_phase_timing.sh -> libtmjx_pt.so; the product library carries no timers).
+14-warp CG kernel in a development build (tools/build_dev_lib.sh pt -DTMJX_PHASE_TIMING -> libtmjx_pt.so; the product library carries no timers).
 
-    bash tools/build_phase_timing.sh && TMJX_LIB_PATH=track-mjx_b200/csrc/libtmjx_pt.so python tools/gpu_phase_timing.py [warps alive]
+    bash tools/build_dev_lib.sh pt -DTMJX_PHASE_TIMING && TMJX_LIB_PATH=track-mjx_b200/csrc/libtmjx_pt.so python tools/gpu_phase_timing.py [warps alive]
 """
 import ctypes as C
 import os
