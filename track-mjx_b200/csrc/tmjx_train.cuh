@@ -17,6 +17,7 @@
  * NCCL all-reduce and tmjx_adam_step see a single tensor.  Every reduction has a fixed order: results are bitwise reproducible.
  * The checker is oracle/mlp_grad.py (float64, equal to torch autograd to 1e-9); tests/test_gpu_train.py states the TF32 tolerance.
  */
+struct BwdScratch;
 namespace tmjx_policy {
 
 constexpr int kTrainLd = 1024;       // row pitch of the gradient-activation buffers (widest layer / padded fan-in)
@@ -261,12 +262,24 @@ struct TrainStack {
   const float* x0 = nullptr;           // the stack's input buffer ([max_rows, ldx0], K padding zero)
   int ldx0 = 0;
   size_t param_base = 0;               // offset of the owning network's parameter vector in the trainer's flat buffers
+  ::BwdScratch* scr = nullptr;    // the owning network's backward scratch
   std::vector<float*> H, A, wp;        // pre-activations, outputs, un-transposed padded weights per layer
   std::vector<int> kNp;                // fan-in padded to the GEMM's N tile (dgrad output width)
   std::vector<CUtensorMap> mapX, mapDH, mapWp, mapXT, mapDHT;
 };
 
 }  // namespace tmjx_policy
+
+// Backward scratch of ONE network.  The policy and the value network each own a set, so that their backward passes (and forwards: the
+// activations are per stack anyway) can run on two streams at once: a 10240-row minibatch gives 80 CTAs per GEMM on 148 SMs, the two
+// networks together fill the machine.
+struct BwdScratch {
+  float* dA[2] = {nullptr, nullptr};   // gradient w.r.t. a layer's output, ping-pong [max_rows, kTrainLd]
+  float* dH = nullptr;                 // gradient w.r.t. a layer's pre-activation [max_rows, kTrainLd]
+  float *xT = nullptr, *dhT = nullptr; // transposed operands of the wgrad GEMM [kTrainLd, rows_ld]
+  float* dWs = nullptr;                // wgrad output: split-K planes of [kpad, npad]
+  float* partial = nullptr;            // per-block column-sum partials
+};
 
 struct TmjxTrainer {
   TmjxPolicy* pol = nullptr;
@@ -275,11 +288,8 @@ struct TmjxTrainer {
   size_t n_pol = 0, n_val = 0;
   float *params = nullptr, *grads = nullptr;
   TrainStack enc, dec, vnet;
-  float* dA[2] = {nullptr, nullptr};   // gradient w.r.t. a layer's output, ping-pong [max_rows, kTrainLd]
-  float* dH = nullptr;                 // gradient w.r.t. a layer's pre-activation [max_rows, kTrainLd]
-  float *xT = nullptr, *dhT = nullptr; // transposed operands of the wgrad GEMM [kTrainLd, rows_ld]
-  float* dWs = nullptr;                // wgrad output: split-K planes of [kpad, npad]
-  float *zeros = nullptr, *partial = nullptr, *eps = nullptr;
+  BwdScratch sp, sv;                   // policy (encoder + decoder) / value network
+  float *zeros = nullptr, *eps = nullptr;
   std::vector<void*> owned;
 };
 
@@ -336,49 +346,50 @@ static int stack_forward(TmjxTrainer* t, TrainStack& s, int rows, bool save, cud
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "forward launch failed");
 }
 
-// backward through one stack.  dY: gradient w.r.t. the stack's output, in t->dA[which] ([rows, kTrainLd], padding columns zero).
-// On return (need_dx) t->dA[*which] holds the gradient w.r.t. the stack's input.
+// backward through one stack.  dY: gradient w.r.t. the stack's output, in scr->dA[which] ([rows, kTrainLd], padding columns zero).
+// On return (need_dx) scr->dA[*which] holds the gradient w.r.t. the stack's input.
 static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, bool need_dx, cudaStream_t st) {
+  BwdScratch& c = *s.scr;
   const int rows32 = (rows + 31) / 32 * 32;
   for (int l = int(s.layers->size()) - 1; l >= 0; --l) {
     Layer& L = (*s.layers)[l];
     float* g = t->grads + s.param_base;
     const size_t m = s.layers->size();
-    const float* dh = t->dA[*which];                          // linear layer: the incoming gradient IS d pre-activation
+    const float* dh = c.dA[*which];                          // linear layer: the incoming gradient IS d pre-activation
     const CUtensorMap* map_dh = &s.mapDH[l + m * (1 + *which)];
     const int nblk = std::min(kBwdBlocks, (rows + kBwdWarps - 1) / kBwdWarps);
     if (L.act) {
-      ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, size_t(kBwdWarps) * 3 * L.npad * 4, st>>>(t->dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale,
-                                                                                            L.ln, t->dH, kTrainLd, t->partial, rows);
+      ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, size_t(kBwdWarps) * 3 * L.npad * 4, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale,
+                                                                                            L.ln, c.dH, kTrainLd, c.partial, rows);
       dim3 rg((L.n + 31) / 32, L.ln ? 3 : 1);
-      colsum_reduce_kernel<<<rg, 256, 0, st>>>(t->partial, nblk, L.n, L.npad, L.n1, g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr,
+      colsum_reduce_kernel<<<rg, 256, 0, st>>>(c.partial, nblk, L.n, L.npad, L.n1, g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr,
                                                 L.ln ? g + L.off_lnb : nullptr);
-      dh = t->dH;
+      dh = c.dH;
       map_dh = &s.mapDH[l];
     } else {
       const int ny = std::min((rows + 7) / 8, 148);
       dim3 cg((L.n + 31) / 32, ny);
-      colsum_partial_kernel<<<cg, 256, 0, st>>>(dh, kTrainLd, L.n, L.npad, t->partial, rows);
-      colsum_reduce_kernel<<<dim3((L.n + 31) / 32, 1), 256, 0, st>>>(t->partial, ny, L.n, L.npad, L.n1, g + L.off_b,
+      colsum_partial_kernel<<<cg, 256, 0, st>>>(dh, kTrainLd, L.n, L.npad, c.partial, rows);
+      colsum_reduce_kernel<<<dim3((L.n + 31) / 32, 1), 256, 0, st>>>(c.partial, ny, L.n, L.npad, L.n1, g + L.off_b,
                                                                         L.n1 < L.n ? g + L.off_b2 : nullptr, nullptr, nullptr);
     }
     // wgrad: dW = x^T dH
     const float* x = l == 0 ? s.x0 : s.A[l - 1];
     const int ldx = l == 0 ? s.ldx0 : (*s.layers)[l - 1].npad;
-    transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, t->xT, t->rows_ld);
-    transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, t->dhT, t->rows_ld);
+    transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, c.xT, t->rows_ld);
+    transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, c.dhT, t->rows_ld);
     // split-K so that the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs: K = the minibatch rows is the long dimension
     const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
     const size_t plane = size_t(L.kpad) * L.npad, fit = (size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2) / plane;
     const int want = std::max(1, std::min(std::min(kWgradMaxSplits, int(fit)), 148 / tiles));
     int planes = 1;
-    int rc = train_gemm(s.mapXT[l], s.mapDHT[l], t->zeros, t->dWs, L.npad, L.k, rows32, L.npad, st, want, size_t(L.kpad) * L.npad, &planes);
+    int rc = train_gemm(s.mapXT[l], s.mapDHT[l], t->zeros, c.dWs, L.npad, L.k, rows32, L.npad, st, want, size_t(L.kpad) * L.npad, &planes);
     if (rc) return rc;
-    unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(t->dWs, L.npad, size_t(L.kpad) * L.npad, planes, L.k, L.n, L.n1,
+    unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(c.dWs, L.npad, size_t(L.kpad) * L.npad, planes, L.k, L.n, L.n1,
                                                                                    g + L.off_w, L.n1 < L.n ? g + L.off_w2 : nullptr);
     // dgrad: dx = dH W^T
     if (l > 0 || need_dx) {
-      rc = train_gemm(*map_dh, s.mapWp[l], t->zeros, t->dA[*which ^ 1], kTrainLd, rows, L.npad, s.kNp[l], st);
+      rc = train_gemm(*map_dh, s.mapWp[l], t->zeros, c.dA[*which ^ 1], kTrainLd, rows, L.npad, s.kNp[l], st);
       if (rc) return rc;
       *which ^= 1;
     }
@@ -433,16 +444,19 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
   PCU(alloc(&t->params, n_all)); PCU(alloc(&t->grads, n_all));
   PCU(cudaMemcpy(t->params, policy_params, t->n_pol * 4, cudaMemcpyHostToDevice));
   PCU(cudaMemcpy(t->params + t->n_pol, value_params, t->n_val * 4, cudaMemcpyHostToDevice));
-  for (int i = 0; i < 2; ++i) PCU(alloc(&t->dA[i], size_t(max_rows) * kTrainLd));
-  PCU(alloc(&t->dH, size_t(max_rows) * kTrainLd));
-  PCU(alloc(&t->xT, size_t(kTrainLd) * t->rows_ld)); PCU(alloc(&t->dhT, size_t(kTrainLd) * t->rows_ld));
-  PCU(alloc(&t->dWs, size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2));   // planes x [kpad, npad]; kpad x npad <= 1024 x 512 for every layer here
-  PCU(alloc(&t->zeros, kTrainLd)); PCU(alloc(&t->partial, size_t(kBwdBlocks) * 3 * kTrainLd));
+  for (BwdScratch* c : {&t->sp, &t->sv}) {
+    for (int i = 0; i < 2; ++i) PCU(alloc(&c->dA[i], size_t(max_rows) * kTrainLd));
+    PCU(alloc(&c->dH, size_t(max_rows) * kTrainLd));
+    PCU(alloc(&c->xT, size_t(kTrainLd) * t->rows_ld)); PCU(alloc(&c->dhT, size_t(kTrainLd) * t->rows_ld));
+    PCU(alloc(&c->dWs, size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2));   // planes x [kpad, npad]; kpad x npad <= 1024 x 512 for every layer here
+    PCU(alloc(&c->partial, size_t(kBwdBlocks) * 3 * kTrainLd));
+  }
+  PCU(alloc(&t->zeros, kTrainLd));
   PCU(alloc(&t->eps, size_t(max_rows) * std::max(1, pd->latent_size)));
   PCU(cudaFuncSetAttribute(ln_silu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * kTrainLd * 4));
   bool ok = true;
-  auto setup = [&](TrainStack& s, std::vector<Layer>& layers, const float* x0, int ldx0, size_t base) -> cudaError_t {
-    s.layers = &layers; s.x0 = x0; s.ldx0 = ldx0; s.param_base = base;
+  auto setup = [&](TrainStack& s, std::vector<Layer>& layers, const float* x0, int ldx0, size_t base, BwdScratch* scr) -> cudaError_t {
+    s.layers = &layers; s.x0 = x0; s.ldx0 = ldx0; s.param_base = base; s.scr = scr;
     const size_t m = layers.size();
     s.H.resize(m); s.A.resize(m); s.wp.resize(m); s.kNp.resize(m);
     s.mapX.resize(m); s.mapDH.resize(3 * m); s.mapWp.resize(m); s.mapXT.resize(m); s.mapDHT.resize(m);
@@ -460,18 +474,18 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
       const int ldx = l == 0 ? ldx0 : layers[l - 1].npad;
       ok = ok && encode_map(&s.mapX[l], x, max_rows, L.kpad, ldx, 256);
       // dgrad A operand = the gradient w.r.t. this layer's pre-activation, K extent npad: from dH (hidden layers) or dA[0/1] (linear)
-      ok = ok && encode_map(&s.mapDH[l], t->dH, max_rows, L.npad, kTrainLd, 256);
-      ok = ok && encode_map(&s.mapDH[l + m], t->dA[0], max_rows, L.npad, kTrainLd, 256);
-      ok = ok && encode_map(&s.mapDH[l + 2 * m], t->dA[1], max_rows, L.npad, kTrainLd, 256);
+      ok = ok && encode_map(&s.mapDH[l], scr->dH, max_rows, L.npad, kTrainLd, 256);
+      ok = ok && encode_map(&s.mapDH[l + m], scr->dA[0], max_rows, L.npad, kTrainLd, 256);
+      ok = ok && encode_map(&s.mapDH[l + 2 * m], scr->dA[1], max_rows, L.npad, kTrainLd, 256);
       ok = ok && encode_map(&s.mapWp[l], s.wp[l], s.kNp[l], L.npad, L.npad, s.kNp[l] >= 512 ? 256 : 128);
-      ok = ok && encode_map(&s.mapXT[l], t->xT, L.kpad, t->rows_ld, t->rows_ld, 256);
-      ok = ok && encode_map(&s.mapDHT[l], t->dhT, L.npad, t->rows_ld, t->rows_ld, L.npad >= 512 ? 256 : 128);
+      ok = ok && encode_map(&s.mapXT[l], scr->xT, L.kpad, t->rows_ld, t->rows_ld, 256);
+      ok = ok && encode_map(&s.mapDHT[l], scr->dhT, L.npad, t->rows_ld, t->rows_ld, L.npad >= 512 ? 256 : 128);
     }
     return cudaSuccess;
   };
-  PCU(setup(t->enc, t->pol->enc, t->pol->enc_in, t->pol->ld_enc, 0));
-  PCU(setup(t->dec, t->pol->dec, t->pol->dec_in, t->pol->ld_dec, 0));
-  PCU(setup(t->vnet, t->val->enc, t->val->enc_in, t->val->ld_enc, t->n_pol));
+  PCU(setup(t->enc, t->pol->enc, t->pol->enc_in, t->pol->ld_enc, 0, &t->sp));
+  PCU(setup(t->dec, t->pol->dec, t->pol->dec_in, t->pol->ld_dec, 0, &t->sp));
+  PCU(setup(t->vnet, t->val->enc, t->val->enc_in, t->val->ld_enc, t->n_pol, &t->sv));
   if (!ok) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
   for (TrainStack* s : {&t->enc, &t->dec}) { rc = repack_layers(*s->layers, t->params, &s->wp, nullptr); if (rc) return rc; }
   rc = repack_layers(*t->vnet.layers, t->params + t->n_pol, &t->vnet.wp, nullptr);
@@ -543,13 +557,13 @@ int tmjx_trainer_policy_backward(TmjxTrainer* t, const float* d_logits, const fl
   const TmjxPolicyDesc& d = t->pol->d;
   int which = 0;
   const Layer& lg = t->dec.layers->back();
-  pad_rows_kernel<<<unsigned((size_t(rows) * lg.npad + 255) / 256), 256, 0, st>>>(d_logits, 2 * d.action_size, t->dA[which], kTrainLd, lg.npad, rows);
+  pad_rows_kernel<<<unsigned((size_t(rows) * lg.npad + 255) / 256), 256, 0, st>>>(d_logits, 2 * d.action_size, t->sp.dA[which], kTrainLd, lg.npad, rows);
   int rc = stack_backward(t, t->dec, rows, &which, true, st);
   if (rc) return rc;
   const Layer& head = t->enc.layers->back();
   const float* headH = t->enc.H[t->enc.layers->size() - 1];
-  latent_bwd_kernel<<<unsigned((size_t(rows) * head.npad + 255) / 256), 256, 0, st>>>(t->dA[which], kTrainLd, d_latent_mean, d_latent_logvar, t->eps, headH,
-                                                                                        head.npad, d.latent_size, t->dA[which ^ 1], kTrainLd, head.npad, rows);
+  latent_bwd_kernel<<<unsigned((size_t(rows) * head.npad + 255) / 256), 256, 0, st>>>(t->sp.dA[which], kTrainLd, d_latent_mean, d_latent_logvar, t->eps, headH,
+                                                                                        head.npad, d.latent_size, t->sp.dA[which ^ 1], kTrainLd, head.npad, rows);
   which ^= 1;
   rc = stack_backward(t, t->enc, rows, &which, false, st);
   if (rc) return rc;
@@ -582,7 +596,7 @@ int tmjx_trainer_value_backward(TmjxTrainer* t, const float* d_value, int rows, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int which = 0;
   const Layer& last = t->vnet.layers->back();
-  pad_rows_kernel<<<unsigned((size_t(rows) * last.npad + 255) / 256), 256, 0, st>>>(d_value, 1, t->dA[which], kTrainLd, last.npad, rows);
+  pad_rows_kernel<<<unsigned((size_t(rows) * last.npad + 255) / 256), 256, 0, st>>>(d_value, 1, t->sv.dA[which], kTrainLd, last.npad, rows);
   int rc = stack_backward(t, t->vnet, rows, &which, false, st);
   if (rc) return rc;
   PCU(cudaGetLastError());

@@ -7,8 +7,9 @@ One `training_step()` is, per GPU (one process per GPU, env shard = contiguous b
      the step kernel and the policy kernels write the `[T, B, ...]` rollout in place)                          ppo.py:330-354
   2. observation-normaliser update over the rollout's observations, two small NCCL all-reduces              ppo.py:357-383
   3. `num_updates_per_batch` epochs x `num_minibatches` minibatches (a fresh env permutation per epoch):     ppo.py:279-318
-     network forward (training mode) -> PPO loss head -> backward -> NCCL all-reduce of the flat gradient (the value-network
-     bucket goes out while the policy backward is still running) -> global-norm clip + Adam -> operand refresh
+     network forward (training mode; policy and critic on two streams) -> PPO loss head -> backward (two streams) -> NCCL all-reduce
+     of the flat gradient (the value-network bucket goes out while the policy backward is still running) -> global-norm clip + Adam ->
+     operand refresh
   4. the acting policy picks the new parameters up in place.
 Torch is the plumbing (device buffers, the permutation gather, `torch.distributed` over NCCL); every FLOP of the networks, the
 loss, the optimiser and the env runs in this repository's kernels.  No CPU fallback.
@@ -75,6 +76,7 @@ class PPO:
         from .sharding import GradientBuckets
 
         self.buckets = GradientBuckets(self.trainer.grads, [self.trainer.n_policy])     # bucket 0 = policy vector, 1 = value vector
+        self.value_stream = torch.cuda.Stream(device=dev)
         self.timing, self.marks = False, []
         self.all_reduce = self.world > 1
 
@@ -100,18 +102,31 @@ class PPO:
         A, Lz = self.net_cfg.action_size, self.net_cfg.latent_size
         eps_z = torch.randn(rows, Lz, device=self.env.device, generator=self.gen)                # policy_key  (losses.py:143, 148-150)
         eps_e = torch.randn(T, Bm, A, device=self.env.device, generator=self.gen)                # entropy_key
-        bootstrap = tr.value_forward(mb["next_obs_last"])                                        # losses.py:154-156 (no gradient reaches it)
+        # The two networks are independent until the loss head and after it: they run on two streams (a 10240-row minibatch is 80 CTAs
+        # per GEMM on 148 SMs; the policy's and the critic's GEMMs together fill the machine), each with its own backward scratch.
+        main = torch.cuda.current_stream(self.env.device)
+        sv = self.value_stream
+        sv.wait_stream(main)
+        with torch.cuda.stream(sv):
+            bootstrap = tr.value_forward(mb["next_obs_last"])                                    # losses.py:154-156 (no gradient reaches it)
+            baseline = tr.value_forward(mb["obs"])
         logits, mean, logvar = tr.policy_forward(mb["obs"], eps_z)
-        baseline = tr.value_forward(mb["obs"])
+        main.wait_stream(sv)
         kl_w = float(self.kl_schedule(self.it)) if self.kl_schedule else c.kl_weight
         out = LN.ppo_loss_head(logits.view(T, Bm, 2 * A), mean.view(T, Bm, Lz), logvar.view(T, Bm, Lz), baseline.view(T, Bm), bootstrap,
                                mb["reward"], mb["discount"], mb["truncation"], mb["raw_action"], mb["log_prob"], eps_e,
                                entropy_cost=c.entropy_cost, kl_weight=kl_w, discounting=c.discounting, reward_scaling=c.reward_scaling,
                                gae_lambda=c.gae_lambda, clipping_epsilon=c.clipping_epsilon, normalize_advantage=c.normalize_advantage)
-        tr.value_backward(out["d_baseline"].reshape(rows))
-        if self.all_reduce:
-            self.buckets.reduce(1)    # value-network bucket: its all-reduce runs on NCCL's stream while the policy backward keeps the SMs busy
+        d_base = out["d_baseline"].reshape(rows)
+        sv.wait_stream(main)
+        with torch.cuda.stream(sv):
+            tr.value_backward(d_base)
+            if self.all_reduce:
+                self.buckets.reduce(1)    # value-network bucket: reduced on NCCL's stream as soon as the critic's backward is done
         tr.policy_backward(out["d_logits"].view(rows, 2 * A), out["d_latent_mean"].view(rows, Lz), out["d_latent_logvar"].view(rows, Lz))
+        main.wait_stream(sv)
+        bootstrap.record_stream(main); baseline.record_stream(main)      # allocator: allocated on the side stream, read by the loss head on main
+        d_base.record_stream(sv)                                         # allocated on main, read by the critic's backward on the side stream
         scale = 1.0
         if self.all_reduce:
             self.buckets.reduce(0)
