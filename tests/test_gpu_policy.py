@@ -238,3 +238,62 @@ def test_value_network_matches_fp32_reference_and_feeds_the_loss_head():
     assert all(np.isfinite(float(out[k])) for k in ("total_loss", "policy_loss", "v_loss", "kl_latent_loss", "entropy_loss"))
     assert out["d_baseline"].shape == (T, B) and out["d_logits"].shape == (T, B, 2 * A) and torch.isfinite(out["d_logits"]).all()
     net.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 130, 777, 1000])
+def test_fused_chain_kernel_matches_the_per_layer_launches(setup, n, monkeypatch):
+    """The one-launch policy (`mlp_chain_kernel`, csrc/tmjx_chain.cuh: TMEM-resident SiLU + LayerNorm epilogue, latent and action rows
+    in the same launch) against the per-layer launches it replaces (TMJX_POLICY_FUSED=0).  Both run the same tcgen05 TF32 MMAs over the
+    same K order, so the pre-activations are bit-identical; the LayerNorm sums are taken in a different order (thread-sequential + four
+    column groups instead of a warp shuffle tree): 1e-6 relative per layer, which flips TF32 operand roundings (2^-11 relative) of the
+    next layer here and there: a few 1e-3 absolute on O(1) logits after eleven layers (raw actions add scale x eps with |eps| up to 4), inside the budget
+    against fp32 (2e-2).  Row counts cover a single partial CTA, a ragged tail and max_env."""
+    from track_mjx_b200.policy import IntentionPolicy
+
+    cfg, p, pol = setup
+    assert pol.launches_per_act == 1
+    monkeypatch.setenv("TMJX_POLICY_FUSED", "0")
+    ref = IntentionPolicy(cfg, p, max_env=1000)
+    assert ref.launches_per_act == 25
+    g = torch.Generator(device="cpu").manual_seed(11 + n)
+    obs = torch.randn(n, cfg.obs_size, generator=g).to(pol.device)
+    ez = torch.randn(n, cfg.latent_size, generator=g).to(pol.device)
+    ea = torch.randn(n, cfg.action_size, generator=g).to(pol.device)
+    for det in (False, True):
+        a0, e0 = ref.act(obs, ez, ea, deterministic=det)
+        a1, e1 = pol.act(obs, ez, ea, deterministic=det)
+        torch.cuda.synchronize()
+        for k in ("latent_mean", "latent_logvar", "logits", "raw_action"):
+            assert torch.isfinite(e1[k]).all()
+            assert (e1[k] - e0[k]).abs().max().item() < (2e-2 if k == "raw_action" else 1e-2), (k, det, (e1[k] - e0[k]).abs().max().item())
+        assert (a1 - a0).abs().max().item() < 1e-2
+        assert (e1["log_prob"] - e0["log_prob"]).abs().max().item() < 2e-2 * max(1.0, e0["log_prob"].abs().max().item())
+    # the fused launch is deterministic and independent of the row's position in the batch
+    a_fwd = pol.act(obs, ez, ea)[0].clone()           # (act returns views into the policy's own buffers)
+    a_rev = pol.act(obs.flip(0).contiguous(), ez.flip(0).contiguous(), ea.flip(0).contiguous())[0].clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a_fwd.flip(0), a_rev)
+    ref.close()
+
+
+@pytest.mark.gpu
+def test_fused_value_chain_matches_the_per_layer_launches(monkeypatch):
+    from track_mjx_b200.policy import ValueNetwork, init_value_params
+
+    rng = np.random.default_rng(5)
+    obs_size, hidden = 696, (512, 512, 512, 512, 512, 256)          # the shipped critic (rodent-full-clips.yaml:54)
+    params = init_value_params(obs_size, hidden, seed=2)
+    params["norm/mean"] = rng.normal(0, 0.5, obs_size).astype(np.float32)
+    params["norm/std"] = rng.uniform(0.5, 2.0, obs_size).astype(np.float32)
+    for i in range(len(hidden) + 1):
+        params[f"hidden_{i}/bias"] = rng.normal(0, 0.1, params[f"hidden_{i}/bias"].shape).astype(np.float32)
+    obs = torch.from_numpy((rng.normal(size=(1111, obs_size)) * 1.5 + 0.3).astype(np.float32)).cuda()
+    fused = ValueNetwork(obs_size, params, max_env=2048, hidden_layers=hidden)
+    monkeypatch.setenv("TMJX_POLICY_FUSED", "0")
+    ref = ValueNetwork(obs_size, params, max_env=2048, hidden_layers=hidden)
+    a, b = fused.apply(obs).clone(), ref.apply(obs).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all() and b.abs().max().item() > 0.05
+    assert (a - b).abs().max().item() < 1e-5 * max(1.0, b.abs().max().item())     # no LayerNorm: same MMAs, same SiLU -> (almost) bitwise
+    fused.close(); ref.close()

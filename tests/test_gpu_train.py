@@ -136,7 +136,9 @@ def test_optimiser_step_reaches_the_acting_policy():
     _, ex0 = pol.act(obs, ez, ea)
     logits0 = ex0["logits"].clone()
     lt, _, _ = tr.policy_forward(obs, ez)
-    assert rel(lt.cpu().numpy(), logits0.cpu().numpy()) < 1e-3          # same kernels, same parameters (LayerNorm / SiLU order differs by rounding)
+    # same parameters, same TF32 MMAs; the acting launch applies LayerNorm through folded weights (csrc/tmjx_chain.cuh), so its TF32 operand
+    # roundings meet s g instead of LN(s): a few 1e-3 of the largest logit after eleven layers, well inside the 2e-2 budget against fp32
+    assert rel(lt.cpu().numpy(), logits0.cpu().numpy()) < 5e-3
     # one optimiser step on a random gradient, then hand the parameters to the actor
     opt = Adam(tr.params, learning_rate=1e-2)
     tr.grads.copy_(torch.randn(tr.n_params, device="cuda", generator=g))

@@ -1139,9 +1139,31 @@ struct Layer {
   int n1 = 0;
   CUtensorMap mapW;                 // [npad rows, kpad] fp32, box 32 x BN, 128-byte swizzle
   CUtensorMap mapX;                 // the layer's input buffer inside tmjx_policy_act ([max_env rows, kpad], box 32 x 256)
+  CUtensorMap mapX128;              // the same buffer with a 32 x 128 box: the fused chain kernel (tmjx_chain.cuh) owns 128 rows per CTA
+  // fused chain kernel, layers whose input is a LayerNorm output: the normalisation is applied THROUGH the weights (tmjx_chain.cuh header):
+  // wt_f[j, i] = wt[j, i] g_prev[i], cvec[j] = sum_i wt[j, i] g_prev[i], bias_f[j] = bias[j] + sum_i wt[j, i] beta_prev[i]
+  float *wt_f = nullptr, *bias_f = nullptr, *cvec = nullptr;
+  CUtensorMap mapWf;
+  CUtensorMap mapWc, mapWfc;        // the weight maps with a 32 x (cw / cluster size) box: a CTA's multicast share of a slice
   const float* x_bound = nullptr;   // the buffer mapX was encoded for
   int ldx_bound = 0;
 };
+
+// LayerNorm of the previous layer folded into this layer's operands (fused chain kernel): one warp per output row j
+__global__ void fold_ln_kernel(const float* __restrict__ wt, const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ beta,
+                               int k, int kpad, int npad, float* __restrict__ wt_f, float* __restrict__ bias_f, float* __restrict__ cvec) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= npad) return;
+  float c = 0.f, b = 0.f;
+  for (int i = lane; i < kpad; i += 32) {
+    const float w = wt[size_t(j) * kpad + i], gi = i < k ? g[i] : 0.f, bi = i < k ? beta[i] : 0.f;
+    wt_f[size_t(j) * kpad + i] = w * gi;
+    c = fmaf(w, gi, c); b = fmaf(w, bi, b);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane == 0) { cvec[j] = c; bias_f[j] = bias[j] + b; }
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1169,12 +1191,16 @@ static bool encode_map(CUtensorMap* m, const float* base, int rows, int cols, in
 
 }  // namespace tmjx_policy
 
+#include "tmjx_chain.cuh"
+
 using namespace tmjx_policy;
 
 struct TmjxPolicy {
   TmjxPolicyDesc d;
   int device = 0, max_env = 0, desc_swap = 0, use_v1 = 0;   // use_v1: 0 = TMA kernel, 1 = 128 x 128 block-synchronous, 2 = cp.async warp-specialised
   int skip_epi = 0;   // timing experiment knob (TMJX_POLICY_SKIP_EPI=1): results are invalid
+  int cluster = 1;    // thread-block cluster size of the fused launch (TMJX_CHAIN_CLUSTER = 1 / 2 / 4): weight slices are multicast inside a cluster
+  int fused = 1;      // one persistent launch per act / value apply (tmjx_chain.cuh); TMJX_POLICY_FUSED=0 keeps the per-layer launches
   std::vector<Layer> enc, dec;   // enc: hidden layers + the fused (mean | logvar) head; dec: hidden layers + logits
   float *norm_mean = nullptr, *norm_std = nullptr;
   float* buf[2] = {nullptr, nullptr};   // ping-pong activations [max_env, ld_buf]
@@ -1182,6 +1208,16 @@ struct TmjxPolicy {
   int ld_buf = 0, ld_enc = 0, ld_dec = 0;
   std::vector<void*> owned;
 };
+
+// (re)compute the folded operands of every layer that follows a LayerNorm layer in its stack; stream-ordered after the weight upload / repack
+static void fold_layers(std::vector<Layer>& layers, cudaStream_t st) {
+  for (size_t l = 1; l < layers.size(); ++l) {
+    Layer& L = layers[l];
+    const Layer& Pv = layers[l - 1];
+    if (!Pv.ln || !L.wt_f) continue;
+    fold_ln_kernel<<<(L.npad + 7) / 8, 256, 0, st>>>(L.wt, L.bias, Pv.ln_scale, Pv.ln_bias, L.k, L.kpad, L.npad, L.wt_f, L.bias_f, L.cvec);
+  }
+}
 
 static thread_local std::string g_perr;
 static int pfail(int code, const std::string& msg) { g_perr = msg; return code; }
@@ -1218,6 +1254,10 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
   if (const char* e = std::getenv("TMJX_POLICY_DESC_SWAP")) p->desc_swap = atoi(e);
   if (const char* e = std::getenv("TMJX_POLICY_V1")) p->use_v1 = atoi(e);
   if (const char* e = std::getenv("TMJX_POLICY_SKIP_EPI")) p->skip_epi = atoi(e) ? 4 : 0;   // A/B knob: the 128 x 128 block-synchronous kernel
+  if (const char* e = std::getenv("TMJX_POLICY_FUSED")) p->fused = atoi(e);
+  if (const char* e = std::getenv("TMJX_CHAIN_CLUSTER")) p->cluster = atoi(e);
+  if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) return pfail(TMJX_E_ARG, "TMJX_CHAIN_CLUSTER must be 1, 2 or 4");
+  if (p->use_v1) p->fused = 0;
   const float* cur = params;
   auto upload = [&](const std::vector<float>& h, float** dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(h.size(), 1) * 4);
@@ -1298,6 +1338,7 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
     auto bind = [&](Layer& L) -> bool {
       if (!encode_map(&L.mapW, L.wt, L.npad, L.kpad, L.kpad, L.npad >= 512 ? 256 : 128)) return false;
       if (!encode_map(&L.mapX, x, max_env, L.kpad, ldx, 256)) return false;
+      if (!encode_map(&L.mapX128, x, max_env, L.kpad, ldx, 128)) return false;
       L.x_bound = x; L.ldx_bound = ldx;
       x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
       return true;
@@ -1305,7 +1346,24 @@ int tmjx_policy_create(const TmjxPolicyDesc* d, const float* params, size_t n_pa
     for (Layer& L : p->enc) if (!bind(L)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
     x = p->dec_in; ldx = p->ld_dec;
     for (Layer& L : p->dec) if (!bind(L)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    for (std::vector<Layer>* stack : {&p->enc, &p->dec}) {
+      for (size_t l = 1; l < stack->size(); ++l) {
+        Layer& L = (*stack)[l];
+        if (!(*stack)[l - 1].ln) continue;
+        PCU(cudaMalloc(&L.wt_f, size_t(L.npad) * L.kpad * 4)); p->owned.push_back(L.wt_f);
+        PCU(cudaMalloc(&L.bias_f, size_t(L.npad) * 4)); p->owned.push_back(L.bias_f);
+        PCU(cudaMalloc(&L.cvec, size_t(L.npad) * 4)); p->owned.push_back(L.cvec);
+        if (!encode_map(&L.mapWf, L.wt_f, L.npad, L.kpad, L.kpad, L.npad >= 512 ? 256 : 128)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+        if (!encode_map(&L.mapWfc, L.wt_f, L.npad, L.kpad, L.kpad, (L.npad >= 512 ? 256 : 128) / p->cluster)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+      }
+      for (Layer& L : *stack)
+        if (!encode_map(&L.mapWc, L.wt, L.npad, L.kpad, L.kpad, (L.npad >= 512 ? 256 : 128) / p->cluster)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+      fold_layers(*stack, nullptr);
+    }
+    PCU(cudaDeviceSynchronize());
   }
+  PCU(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+  if (int(p->enc.size() + p->dec.size()) > kChainMaxLayers) p->fused = 0;
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<256>::kSmem));
   PCU(cudaFuncSetAttribute(linear_tf32_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2<128>::kSmem));
   *out = guard.release();
@@ -1347,6 +1405,43 @@ static int run_linear(const TmjxPolicy* p, const Layer& L, const float* x, int l
   return TMJX_OK;
 }
 
+static long long* g_chain_trace = nullptr;   // development only: tmjx_policy_chain_trace
+// the layer list of a policy / value network as the fused chain kernel wants it: buffers in the ping-pong order the tensor maps were bound in
+static void chain_fill(const TmjxPolicy* p, ChainParams& cp) {
+  static_assert(sizeof(ChainParams) < 32000, "kernel parameter space");
+  int pp = 0, i = 0;
+  auto add = [&](const Layer& L) {
+    ChainLayer& c = cp.L[i++];
+    c.mapX = L.mapX128;
+    if (L.wt_f) { c.mapW = p->cluster > 1 ? L.mapWfc : L.mapWf; c.bias = L.bias_f; c.cvec = L.cvec; }
+    else { c.mapW = p->cluster > 1 ? L.mapWc : L.mapW; c.bias = L.bias; c.cvec = nullptr; }
+    c.out = p->buf[pp]; c.ldo = p->ld_buf; c.save_h = nullptr; c.ldh = 0;
+    c.kpad = L.kpad; c.npad = L.npad; c.n = L.n; c.cw = L.npad >= 512 ? 256 : 128; c.act = L.act; c.ln = L.ln; c.kind = 0;
+    pp ^= 1;
+  };
+  for (const Layer& L : p->enc) add(L);
+  for (const Layer& L : p->dec) add(L);
+  cp.n_layers = i;
+  cp.csz = p->cluster;
+  if (const char* e = std::getenv("TMJX_CHAIN_DBG")) cp.dbg = atoi(e);
+  if (const char* e = std::getenv("TMJX_CHAIN_STAGGER_NS")) cp.stagger_ns = unsigned(atoi(e));
+  cp.trace = g_chain_trace;
+}
+
+// one launch of the fused chain: ceil(M / 128) CTAs rounded up to whole clusters (the spare CTAs of the last cluster run on rows >= M:
+// out-of-range TMA boxes read zeros, every store is guarded)
+static int launch_chain(const ChainParams& cp, int n_env, cudaStream_t st) {
+  const int csz = cp.csz, ctas = ((n_env + 127) / 128 + csz - 1) / csz * csz;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(ctas)); cfg.blockDim = dim3(kChainThreads); cfg.dynamicSmemBytes = kChainSmem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(csz); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = csz > 1 ? 1 : 0;
+  PCU(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, cp));
+  return TMJX_OK;
+}
+
 /* plain GEMM entry point (tests, microbenchmarks): y[M, ldy] = x[M, k] * W + b through the same tcgen05 kernel */
 int tmjx_policy_linear(const TmjxPolicy* p, int which /* 0.. : encoder layers then decoder layers */, const float* x, int ldx, float* y, int ldy,
                        int n_env, void* stream) {
@@ -1367,6 +1462,19 @@ int tmjx_policy_act(const TmjxPolicy* p, const float* obs, const float* eps_late
   PCU(cudaSetDevice(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TmjxPolicyDesc& d = p->d;
+  if (p->fused) {   // ONE launch: normalise -> encoder -> latent -> decoder -> action rows (tmjx_chain.cuh)
+    ChainParams cp;
+    std::memset(&cp, 0, sizeof(cp));
+    chain_fill(p, cp);
+    cp.M = n_env;
+    cp.obs = obs; cp.nobs = d.obs_size; cp.nref = d.reference_obs_size; cp.latent = d.latent_size;
+    cp.mean = p->norm_mean; cp.stdv = p->norm_std; cp.enc_in = p->enc_in; cp.ld_enc = p->ld_enc; cp.dec_in = p->dec_in; cp.ld_dec = p->ld_dec;
+    cp.eps_latent = eps_latent; cp.deterministic = deterministic; cp.out_mean = latent_mean; cp.out_logvar = latent_logvar;
+    cp.na = d.action_size; cp.eps_action = eps_action; cp.action = action; cp.raw_action = raw_action; cp.log_prob = log_prob; cp.logits = logits;
+    cp.L[p->enc.size() - 1].kind = 1;
+    cp.L[cp.n_layers - 1].kind = 2;
+    return launch_chain(cp, n_env, st);
+  }
   obs_prep_kernel<<<n_env, 256, 0, st>>>(obs, d.obs_size, d.reference_obs_size, d.latent_size, p->norm_mean, p->norm_std, p->enc_in, p->ld_enc,
                                          p->dec_in, p->ld_dec, n_env);
   const float* x = p->enc_in;
@@ -1445,9 +1553,17 @@ int tmjx_value_create(const TmjxValueDesc* d, const float* params, size_t n_para
   for (Layer& L : p->enc) {
     if (!encode_map(&L.mapW, L.wt, L.npad, L.kpad, L.kpad, L.npad >= 512 ? 256 : 128)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
     if (!encode_map(&L.mapX, x, max_env, L.kpad, ldx, 256)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+    if (!encode_map(&L.mapX128, x, max_env, L.kpad, ldx, 128)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
     L.x_bound = x; L.ldx_bound = ldx;
     x = p->buf[pp]; ldx = p->ld_buf; pp ^= 1;
   }
+  PCU(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+  if (const char* e = std::getenv("TMJX_POLICY_FUSED")) p->fused = atoi(e);
+  if (const char* e = std::getenv("TMJX_CHAIN_CLUSTER")) p->cluster = atoi(e);
+  if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) return pfail(TMJX_E_ARG, "TMJX_CHAIN_CLUSTER must be 1, 2 or 4");
+  for (Layer& L : p->enc)
+    if (!encode_map(&L.mapWc, L.wt, L.npad, L.kpad, L.kpad, (L.npad >= 512 ? 256 : 128) / p->cluster)) return pfail(TMJX_E_CUDA, "cuTensorMapEncodeTiled failed");
+  if (int(p->enc.size()) > kChainMaxLayers) p->fused = 0;
   *out = guard.release();
   return TMJX_OK;
 }
@@ -1457,6 +1573,16 @@ int tmjx_value_apply(const TmjxPolicy* v, const float* obs, float* value, int n_
   if (n_env <= 0 || n_env > v->max_env) return pfail(TMJX_E_ARG, "n_env exceeds the network's max_env");
   PCU(cudaSetDevice(v->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (v->fused) {
+    ChainParams cp;
+    std::memset(&cp, 0, sizeof(cp));
+    chain_fill(v, cp);
+    cp.M = n_env;
+    cp.obs = obs; cp.nobs = v->d.obs_size; cp.nref = v->d.obs_size; cp.mean = v->norm_mean; cp.stdv = v->norm_std; cp.enc_in = v->enc_in; cp.ld_enc = v->ld_enc;
+    cp.value = value;
+    cp.L[cp.n_layers - 1].kind = 3;
+    return launch_chain(cp, n_env, st);
+  }
   value_prep_kernel<<<n_env, 256, 0, st>>>(obs, v->d.obs_size, v->norm_mean, v->norm_std, v->enc_in, v->ld_enc, n_env);
   const float* x = v->enc_in;
   int ldx = v->ld_enc, pp = 0;
@@ -1586,8 +1712,19 @@ int tmjx_running_stats_apply(const float* var, int D, float std_min, float std_m
   return TMJX_OK;
 }
 
+/* development: per-layer clock64() marks of CTA 0 of the fused chain launch (tools/gpu_chain_trace.py).  enable != 0 allocates / arms the
+ * buffer, out != null copies the 8 marks x kChainMaxLayers back.  Not part of the product surface (not declared in include/tmjx.h). */
+int tmjx_policy_chain_trace(int enable, long long* out) {
+  if (enable && !g_chain_trace) { PCU(cudaMalloc(&g_chain_trace, 8 * kChainMaxLayers * sizeof(long long))); }
+  if (enable) PCU(cudaMemset(g_chain_trace, 0, 8 * kChainMaxLayers * sizeof(long long)));
+  if (out && g_chain_trace) PCU(cudaMemcpy(out, g_chain_trace, 8 * kChainMaxLayers * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (!enable && !out && g_chain_trace) { cudaFree(g_chain_trace); g_chain_trace = nullptr; }
+  return TMJX_OK;
+}
+
 int tmjx_policy_launches_per_act(const TmjxPolicy* p) {
   if (!p) return 0;
+  if (p->fused) return 1;
   int n = 3;   // obs_prep, latent, action_head
   for (const Layer& L : p->enc) n += 1 + L.ln;
   for (const Layer& L : p->dec) n += 1 + L.ln;

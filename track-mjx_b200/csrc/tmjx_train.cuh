@@ -410,7 +410,11 @@ int tmjx_policy_set_params(TmjxPolicy* p, const float* params_device, void* stre
   copy_kernel<<<(D + 255) / 256, 256, 0, st>>>(params_device + D, p->norm_std, D);
   int rc = repack_layers(p->enc, params_device, nullptr, st);
   if (rc) return rc;
-  return repack_layers(p->dec, params_device, nullptr, st);
+  rc = repack_layers(p->dec, params_device, nullptr, st);
+  if (rc) return rc;
+  fold_layers(p->enc, st);     // the fused chain kernel's LayerNorm-folded operands follow the new weights
+  fold_layers(p->dec, st);
+  return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "fold launch failed");
 }
 
 void tmjx_trainer_destroy(TmjxTrainer* t) {
