@@ -260,15 +260,14 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_step(i, st):
         if policy is None:
-            d_act.copy_(h_act[i % 4], non_blocking=True)
-            a = d_act
-        else:   # the policy consumes the device-resident observation; its Gaussian noise comes from pinned host memory
-            d_ez.copy_(h_ez[i % 4], non_blocking=True)
-            d_ea.copy_(h_ea[i % 4], non_blocking=True)
-            a = policy.act(st.obs, d_ez, d_ea)[0]
+            # host actions in, host obs / reward / done out through the env's host-buffer entry point: the batch is cut at lock-step round
+            # boundaries so that the device->host copy of the first part overlaps the step kernel of the second (env.step_host)
+            return env.step_host(st, h_act[i % 4], h_obs, h_rew, h_done)
+        # the policy consumes the device-resident observation; its Gaussian noise comes from pinned host memory, the host reads the metrics
+        d_ez.copy_(h_ez[i % 4], non_blocking=True)
+        d_ea.copy_(h_ea[i % 4], non_blocking=True)
+        a = policy.act(st.obs, d_ez, d_ea)[0]
         st = env.step(st, a)
-        if policy is None:   # with the policy in the loop the observation is consumed on the device; the host reads the metrics
-            h_obs.copy_(st.obs, non_blocking=True)
         h_rew.copy_(st.reward, non_blocking=True)
         h_done.copy_(st.done, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller needs the host results before the next action

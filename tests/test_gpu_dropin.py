@@ -100,3 +100,28 @@ def test_step_before_reset_after_wrap_raises_and_bad_indices_clamp(walker, clips
         env.reset_from_clip(g, {"clip_idx": torch.zeros(4, device=env.device), "start_frame": info["start_frame"]})
     env2 = MultiClipTracking(clips2, walker, config.RewardConfig(), num_envs=2, device=torch.device("cuda"), **config.DEFAULT_ENV_ARGS)
     assert env2.device.index is not None and torch.isfinite(env2.reset(0).obs).all()
+
+
+def test_step_host_equals_step_bit_for_bit(walker, clips2):
+    """`step_host` (host buffers in / out; the batch cut at lock-step round boundaries so that the device->host copy of the first part
+    overlaps the step kernel of the second) against the plain `step` on a twin env: two launches of 2072 + 128 envs give exactly the
+    bits of one launch of 2200 (the step kernel's results are independent of the grid), and the host buffers hold what the device
+    state holds.  Runs under the fused auto-reset wrapper, which is what the bench's end-to-end arm steps."""
+    n = 2200
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    a, b = wrap(make_env(walker, clips2, n)), wrap(make_env(walker, clips2, n))
+    assert n > sm * a.stepper.dims["envs_per_block"]                  # more than one round: the batch IS cut
+    sa, sb = a.reset(5), b.reset(5)
+    assert torch.equal(sa.obs, sb.obs)
+    h_obs, h_rew, h_done = (torch.empty(n, a.observation_size).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n).pin_memory())
+    g = torch.Generator().manual_seed(0)
+    for t in range(4):
+        h_act = (0.3 * torch.randn(n, a.action_size, generator=g)).pin_memory()
+        sa = a.step(sa, h_act.cuda())
+        sb = b.step_host(sb, h_act, h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        for k in ("qpos", "qvel", "obs", "reward", "done", "metrics", "cur_frame", "steps", "action_buffer"):
+            assert torch.equal(a.stepper.buf[k], b.stepper.buf[k]), (t, k)
+        assert torch.equal(h_obs, sb.obs.cpu()) and torch.equal(h_rew, sb.reward.cpu()) and torch.equal(h_done, sb.done.cpu())
+    with pytest.raises(ValueError):
+        b.step_host(sb, h_act, h_obs[:10], h_rew, h_done)

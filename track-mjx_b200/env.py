@@ -136,6 +136,29 @@ class Stepper:
         L.check(self.lib, self.lib.tmjx_step(self._model, self._clips, C.c_void_p(action.data_ptr()), C.byref(self._state_c),
                                              C.byref(self._out_c), self.n_env, flags, self._stream()), "tmjx_step")
 
+    def _range_structs(self, lo: int, hi: int):
+        """TmjxState / TmjxOut whose pointers start at env `lo` (every per-env buffer is `[n_env, width]` row-major)."""
+        key = (lo, hi, self.buf["obs"].data_ptr())
+        cache = self.__dict__.setdefault("_range_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            off = lambda t: t[lo:].data_ptr() if lo < t.shape[0] else t.data_ptr()
+            cache[key] = (L.fill_struct(L.StateC(), L.STATE_FIELDS, self.buf, off), L.fill_struct(L.OutC(), L.OUT_FIELDS + L.DEBUG_FIELDS, self.buf, off))
+        return cache[key]
+
+    def step_range(self, action: torch.Tensor, lo: int, hi: int, flags: int = 0):
+        """Step the environments `lo <= e < hi` only (`action` is the full `[n_env, nu]` device tensor).  Results are independent of how
+        the batch is cut into launches (no cross-env communication, fixed-order arithmetic): `MultiClipTracking.step_host` uses this to
+        copy the first part of a batch to the host while the second part is still in the step kernel."""
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device or action.shape != (self.n_env, self.dims["nu"]):
+            raise ValueError(f"action must be a contiguous fp32 ({self.n_env}, {self.dims['nu']}) tensor on {self.device}")
+        if not 0 <= lo < hi <= self.n_env:
+            raise ValueError("bad env range")
+        st, out = self._range_structs(lo, hi)
+        L.check(self.lib, self.lib.tmjx_step(self._model, self._clips, C.c_void_p(action[lo:].data_ptr()), C.byref(st), C.byref(out), hi - lo, flags,
+                                             self._stream()), "tmjx_step")
+
     def redirect_obs(self, obs: torch.Tensor | None = None):
         """Point TmjxOut.obs at a caller-owned `[n_env, obs_size]` tensor (e.g. slot t+1 of a rollout buffer) so that the step
         kernel writes the observation where its consumer wants it; `None` restores the stepper's own buffer."""
@@ -270,6 +293,47 @@ class MultiClipTracking:
             raise RuntimeError("wrap(env) was applied after the last reset: the auto-reset wrapper has no first_* snapshot to restore "
                                "(the reference takes it in the wrapper's reset, wrappers.py:281-286); call env.reset(...) again")
         self.stepper.step(action, L.TMJX_F_AUTORESET if self._autoreset else 0)
+        return self._state()
+
+    def step_host(self, state: State, h_action: torch.Tensor, h_obs: torch.Tensor, h_reward: torch.Tensor, h_done: torch.Tensor,
+                  parts: int = 2) -> State:
+        """`step` for a caller whose actions and results live in (pinned) HOST memory -- the situation of a host-side policy or of the
+        reference's own API boundary.  Copies the actions in, steps, and copies obs / reward / done out, with the batch cut at lock-step
+        round boundaries of the step kernel (one round = SM count x environments per block) so that the device->host copy of the first
+        part overlaps the kernel of the next one.  Returns when the host buffers are valid.  Same results as `step` (the step kernel's
+        results do not depend on how the batch is cut into launches)."""
+        if self._autoreset and not self._snapshot_taken:
+            raise RuntimeError("wrap(env) was applied after the last reset; call env.reset(...) again")
+        n, sp = self.num_envs, self.stepper
+        for name, t, shape in (("h_action", h_action, (n, self.action_size)), ("h_obs", h_obs, (n, self.observation_size)), ("h_reward", h_reward, (n,)),
+                               ("h_done", h_done, (n,))):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"{name} must be a contiguous fp32 host tensor of shape {shape}")
+        if not hasattr(self, "_host"):
+            props = torch.cuda.get_device_properties(self.device)
+            self._host = {"act": torch.empty(n, self.action_size, device=self.device), "copy": torch.cuda.Stream(device=self.device),
+                          "round": props.multi_processor_count * int(sp.dims.get("envs_per_block", 14))}
+        h = self._host
+        main = torch.cuda.current_stream(self.device)
+        h["act"].copy_(h_action, non_blocking=True)
+        rounds = -(-n // h["round"])
+        parts = max(1, min(parts, rounds))
+        cuts = [min(n, -(-rounds * p // parts) * h["round"]) for p in range(parts + 1)]
+        flags = L.TMJX_F_AUTORESET if self._autoreset else 0
+        b = sp.buf
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            if hi <= lo:
+                continue
+            sp.step_range(h["act"], lo, hi, flags)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(h["copy"]):
+                h["copy"].wait_event(ev)
+                h_obs[lo:hi].copy_(b["obs"][lo:hi], non_blocking=True)
+                h_reward[lo:hi].copy_(b["reward"][lo:hi, 0], non_blocking=True)
+                h_done[lo:hi].copy_(b["done"][lo:hi, 0], non_blocking=True)
+        h["copy"].synchronize()
+        main.wait_stream(h["copy"])
         return self._state()
 
     def _state(self) -> State:
