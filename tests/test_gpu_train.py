@@ -152,7 +152,7 @@ def test_optimiser_step_reaches_the_acting_policy():
     _, ex1 = pol.act(obs, ez, ea)
     assert rel(ex1["logits"].cpu().numpy(), logits0.cpu().numpy()) > 1e-2          # the actor really changed
     lt1, _, _ = tr.policy_forward(obs, ez)
-    assert rel(lt1.cpu().numpy(), ex1["logits"].cpu().numpy()) < 1e-3              # and agrees with the learner's forward
+    assert rel(lt1.cpu().numpy(), ex1["logits"].cpu().numpy()) < 5e-3              # and agrees with the learner's forward (folded-LayerNorm rounding, see above)
     # a policy created from scratch with the updated parameters gives the same bits as the refreshed one
     pol_p, _ = split_flat(cfg, tr.params.cpu().numpy(), VALUE_LAYERS)
     fresh = P.IntentionPolicy(cfg, pol_p, max_env=rows)

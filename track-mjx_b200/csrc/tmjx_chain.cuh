@@ -204,26 +204,6 @@ __device__ __forceinline__ void action_rows_flat(const float* lg, int ld, int na
   __syncwarp();
 }
 
-// this thread's 32 values (row = TMEM lane, columns col .. col + 31) -> global, transposed through the warp's shared-memory tile so that
-// every store instruction writes four complete 128-byte row segments (the direct form -- one 16-byte piece per lane, 32 rows per
-// instruction -- made the epilogue LSU-bound: 16 k scattered requests per layer and CTA).
-__device__ __forceinline__ void store_tile(const uint32_t (&v)[32], float* tile, int lane, float* __restrict__ g, int ld, size_t row0, int rows_valid,
-                                           int col) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)   // row `lane`, chunk j -> chunk slot j ^ (lane & 7): a quarter-warp's eight 16-byte stores hit eight different bank groups
-    *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-  __syncwarp();
-  const int ch = lane & 7, rs = lane >> 3;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rs;
-    const float4 t = *reinterpret_cast<const float4*>(tile + r * 32 + ((ch ^ (r & 7)) << 2));
-    if (r < rows_valid) *reinterpret_cast<float4*>(g + (row0 + r) * ld + col + ch * 4) = t;
-  }
-  __syncwarp();
-}
-
 __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kChainStages], bar_empty[kChainStages], bar_free[kChainStages], bar_tfull[2], bar_tempty[2], bar_cready[4];

@@ -12,7 +12,7 @@
  * NVIDIA GPUs is TF32 as well).  Three kernels live here, newest first:
  *   linear_tf32_tma_kernel<BN>  (default)  256 x BN tile = two M = 128 accumulators sharing one B tile, operands moved by TMA
  *                                (cp.async.bulk.tensor.2d, 128-byte swizzle, expect_tx mbarriers), one producer thread, one MMA
- *                                thread, 16-warp tcgen05.ld epilogue (bias, SiLU);
+ *                                thread, 16-warp tcgen05.ld epilogue (bias, SiLU) with coalesced stores through a swizzled smem transpose;
  *   linear_tf32_v2_kernel<BN>   (TMJX_POLICY_V1=2)  the same tile with warp-specialised cp.async producers;
  *   linear_tf32_kernel          (TMJX_POLICY_V1=1)  128 x 128 tile, block-synchronous cp.async ring.
  * The older two are kept as A/B references (DESIGN.md 3b has the measurements that led from one to the next).  LayerNorm,
@@ -349,6 +349,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                : "memory");
 }
 
+// this thread's 32 values (row = TMEM lane, columns col .. col + 31) -> global, transposed through the warp's shared-memory tile so that
+// every store instruction writes four complete 128-byte row segments (the direct form -- one 16-byte piece per lane, 32 rows per
+// instruction -- made the epilogue LSU-bound: 16 k scattered requests per layer and CTA).
+__device__ __forceinline__ void store_tile(const uint32_t (&v)[32], float* tile, int lane, float* __restrict__ g, int ld, size_t row0, int rows_valid,
+                                           int col) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)   // row `lane`, chunk j -> chunk slot j ^ (lane & 7): a quarter-warp's eight 16-byte stores hit eight different bank groups
+    *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int ch = lane & 7, rs = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rs;
+    const float4 t = *reinterpret_cast<const float4*>(tile + r * 32 + ((ch ^ (r & 7)) << 2));
+    if (r < rows_valid) *reinterpret_cast<float4*>(g + (row0 + r) * ld + col + ch * 4) = t;
+  }
+  __syncwarp();
+}
+
 template <int BN2>
 __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
                                                                      const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
@@ -358,8 +378,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[STG], bar_empty[STG], bar_done;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float sbias[BN2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+  if (tid < BN2) sbias[tid] = __ldg(bias + n0 + tid);   // read by every epilogue thread: broadcast LDS instead of L2-latency loads (the L1 is ~30 KB here)
   // split-K (the wgrad GEMMs of the backward pass: small M x N, K = the minibatch rows): block z accumulates K slices
   // [z nk_per_split, (z + 1) nk_per_split) into its own output plane Y + z y_split_stride; the planes are summed in z order later
   int nk = Kpad / BK, kt0 = 0;
@@ -426,11 +448,15 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
 
-  // ---- epilogue, 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 of accumulator (w / 4) % 2, column half w / 8;
-  // thread = one output row.  (Four warps per scheduler: with two, the bias / SiLU chain was latency-bound and the epilogue
-  // took as long as the main loop; a shared-memory transpose for 128-byte stores measured slower than the direct form.)
+  // ---- epilogue, 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 of accumulator (w / 4) % 2, column half w / 8; thread = one
+  // output row.  Stores go through a per-warp 32 x 32 XOR-swizzled transpose tile (aliased onto the operand stages, which are dead once
+  // bar_done has fired) so that every store instruction writes four complete 128-byte row segments: the direct form -- one 16-byte
+  // piece per lane, 32 rows per instruction -- is LSU-request-bound (measured in the fused chain kernel: 16 k requests, 19 us per
+  // 128 x 512 tile) and made this epilogue longer than the main loop.
   const int h = (warp >> 2) & 1, lane_base = (warp & 3) * 32, chalf = warp >> 3;
-  const int row = m0 + h * 128 + lane_base + lane;
+  const size_t row0 = size_t(m0) + h * 128 + lane_base;
+  const int rows_valid = max(0, min(32, M - int(row0)));
+  float* tile = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw))) + warp * 1024;
   const int c_beg = chalf * (BN2 / 2), c_end = (act & 4) ? c_beg : c_beg + BN2 / 2;   // bit 2: timing experiment only (skip the epilogue)
   act &= 1;
 #pragma unroll 1
@@ -447,21 +473,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row < M) {
-      float* dst = Y + size_t(row) * ldy + n0 + c;
-      const float4* bb = reinterpret_cast<const float4*>(bias + n0 + c);
+    const float4* bb = reinterpret_cast<const float4*>(sbias + c);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(bb + (j >> 2));
-        float4 o;
-        o.x = __uint_as_float(v[j]) + b4.x;
-        o.y = __uint_as_float(v[j + 1]) + b4.y;
-        o.z = __uint_as_float(v[j + 2]) + b4.z;
-        o.w = __uint_as_float(v[j + 3]) + b4.w;
-        if (act) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
-        *reinterpret_cast<float4*>(dst + j) = o;
-      }
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = bb[j >> 2];
+      float4 o;
+      o.x = __uint_as_float(v[j]) + b4.x;
+      o.y = __uint_as_float(v[j + 1]) + b4.y;
+      o.z = __uint_as_float(v[j + 2]) + b4.z;
+      o.w = __uint_as_float(v[j + 3]) + b4.w;
+      if (act) { o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w); }
+      v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y); v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
     }
+    store_tile(v, tile, lane, Y, ldy, row0, rows_valid, n0 + c);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -21,7 +21,7 @@ struct BwdScratch;
 namespace tmjx_policy {
 
 constexpr int kTrainLd = 1024;       // row pitch of the gradient-activation buffers (widest layer / padded fan-in)
-constexpr int kBwdWarps = 4;         // warps per block of the row kernels (4 x 3 x 1024 floats of column accumulators = 48 KB)
+constexpr int kBwdWarps = 8;         // warps per block of the row kernels (8 x 3 x 1024 floats of column accumulators = 96 KB; 4 warps left the SMs at 8 resident warps: latency-bound)
 constexpr int kBwdBlocks = 296;      // 2 x 148: partial column sums per block, reduced in a fixed order
 constexpr int kWgradMaxSplits = 64;  // split-K planes of the wgrad GEMM (scratch: kWgradMaxSplits x the largest padded kernel)
 
