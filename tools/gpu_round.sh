@@ -27,6 +27,8 @@ import json,sys; d=json.load(open('$OUT/${TAG}_$f.json')); print('$f', round(d['
 timeout 600 python tools/gpu_warp_scaling.py > $OUT/${TAG}_warp_scaling.txt 2>&1
 if [ -f track-mjx_b200/csrc/libtmjx_pt.so ]; then for k in 1 14; do timeout 300 python tools/gpu_phase_timing.py $k; done > $OUT/${TAG}_phase_timing.txt 2>&1; fi
 timeout 300 python tools/gpu_learner_bench.py > $OUT/${TAG}_learner_bench.json 2> $OUT/${TAG}_learner_bench.err
+timeout 300 python tools/gpu_policy_bench.py 16384 > $OUT/${TAG}_policy_bench.json 2>> $OUT/${TAG}_learner_bench.err
+timeout 300 python tools/gpu_chain_trace.py 2>&1 | grep -v Warn > $OUT/${TAG}_chain_timeline.txt
 if [ -z "$2" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
       --log-file $OUT/${TAG}_launches_learner.csv python tools/gpu_learner_bench.py --quick > $OUT/${TAG}_ncu_learner.log 2>&1
@@ -37,4 +39,7 @@ if [ -z "$2" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:tmjx_env_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
   ls -la $OUT/${TAG}_prof.ncu-rep
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_chain -s 6 -c 1 -f -o $OUT/${TAG}_chain_prof python tools/gpu_policy_bench.py 16384 > $OUT/${TAG}_chain_ncu.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file $OUT/${TAG}_launches_intention.csv \
+      python bench.py --workload intention --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launch_intention.log 2>&1
 fi

@@ -60,6 +60,105 @@ __global__ void silu_ln_fwd_kernel(const float* __restrict__ H, int ldh, int n, 
 //   s = SiLU(h), shat = (s - mean) rstd, g = dA scale:   ds = rstd (g - mean(g) - shat mean(g shat)),   dh = ds SiLU'(h)
 // Column sums (d Dense bias = sum dh, d LN scale = sum dA shat, d LN bias = sum dA) are accumulated per warp in shared memory in
 // row order, the warps of a block are added in warp order and the block's partial goes to partial[block][3][npad].
+// Register form of ln_silu_bwd_kernel for rows of at most 128 NCH columns (every hidden layer of the shipped networks but the encoder's
+// 1024): a lane keeps its NCH float4 chunks of h and dA in registers, so the row is read ONCE and SiLU / sigmoid are evaluated once
+// (the shared-memory form below makes three passes over h and read-modify-writes three column accumulators per element through
+// shared memory); the column sums live in registers over the warp's rows and meet in shared memory once, in warp order, at the end.
+template <int NCH>
+__global__ void __launch_bounds__(32 * kBwdWarps) ln_silu_bwd_reg_kernel(const float* __restrict__ dA, int ldda, const float* __restrict__ H, int ldh,
+                                                                          int n, int npad, const float* __restrict__ scale, int has_ln,
+                                                                          float* __restrict__ dH, int lddh, float* __restrict__ partial, int M) {
+  extern __shared__ float acc[];   // [kBwdWarps][3][npad], written once
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_n = 1.f / float(n);
+  float sc[NCH][4], ab[NCH][4], as_[NCH][4], al[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int i = lane * 4 + 128 * k;
+    float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (has_ln && i < n) v = *reinterpret_cast<const float4*>(scale + i);
+    sc[k][0] = v.x; sc[k][1] = v.y; sc[k][2] = v.z; sc[k][3] = v.w;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ab[k][c] = as_[k][c] = al[k][c] = 0.f;
+  }
+  for (int row = blockIdx.x * kBwdWarps + warp; row < M; row += gridDim.x * kBwdWarps) {
+    const float* h = H + size_t(row) * ldh;
+    const float* da = dA + size_t(row) * ldda;
+    float* dh = dH + size_t(row) * lddh;
+    float hv[NCH][4], dv[NCH][4], sg[NCH][4];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int i = lane * 4 + 128 * k;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (i < n) { a = *reinterpret_cast<const float4*>(h + i); b = *reinterpret_cast<const float4*>(da + i); }
+      hv[k][0] = a.x; hv[k][1] = a.y; hv[k][2] = a.z; hv[k][3] = a.w;
+      dv[k][0] = b.x; dv[k][1] = b.y; dv[k][2] = b.z; dv[k][3] = b.w;
+    }
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sg[k][c] = sigmoid_fast(hv[k][c]);
+        const float a = lane * 4 + 128 * k < n ? hv[k][c] * sg[k][c] : 0.f;
+        s += a; s2 = fmaf(a, a, s2);
+      }
+    float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
+    if (has_ln) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      mean = s * inv_n;
+      rstd = rsqrtf(fmaxf(0.f, s2 * inv_n - mean * mean) + 1e-6f);
+      float g1 = 0.f, g2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (lane * 4 + 128 * k >= n) continue;
+          const float shat = (hv[k][c] * sg[k][c] - mean) * rstd, g = dv[k][c] * sc[k][c];
+          g1 += g; g2 = fmaf(g, shat, g2);
+          as_[k][c] = fmaf(dv[k][c], shat, as_[k][c]);   // d LN scale
+          al[k][c] += dv[k][c];                          // d LN bias
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { g1 += __shfl_xor_sync(0xffffffffu, g1, o); g2 += __shfl_xor_sync(0xffffffffu, g2, o); }
+      m1 = g1 * inv_n; m2 = g2 * inv_n;
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int i = lane * 4 + 128 * k;
+      if (i >= npad) continue;
+      float o4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (i < n) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float ds = dv[k][c];
+          if (has_ln) { const float shat = (hv[k][c] * sg[k][c] - mean) * rstd; ds = rstd * (dv[k][c] * sc[k][c] - m1 - shat * m2); }
+          o4[c] = ds * (sg[k][c] * (1.f + hv[k][c] * (1.f - sg[k][c])));
+          ab[k][c] += o4[c];                               // d Dense bias
+        }
+      }
+      *reinterpret_cast<float4*>(dh + i) = make_float4(o4[0], o4[1], o4[2], o4[3]);   // padding columns (n <= i < npad) stay zero for the GEMMs
+    }
+  }
+  float* my = acc + size_t(warp) * 3 * npad;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int i = lane * 4 + 128 * k;
+    if (i >= npad) continue;
+    *reinterpret_cast<float4*>(my + i) = make_float4(ab[k][0], ab[k][1], ab[k][2], ab[k][3]);
+    *reinterpret_cast<float4*>(my + npad + i) = make_float4(as_[k][0], as_[k][1], as_[k][2], as_[k][3]);
+    *reinterpret_cast<float4*>(my + 2 * npad + i) = make_float4(al[k][0], al[k][1], al[k][2], al[k][3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * npad; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < kBwdWarps; ++w2) t += acc[size_t(w2) * 3 * npad + i];
+    partial[size_t(blockIdx.x) * 3 * npad + i] = t;
+  }
+}
+
 __global__ void __launch_bounds__(32 * kBwdWarps) ln_silu_bwd_kernel(const float* __restrict__ dA, int ldda, const float* __restrict__ H, int ldh,
                                                                       int n, int npad, const float* __restrict__ scale, int has_ln,
                                                                       float* __restrict__ dH, int lddh, float* __restrict__ partial, int M) {
@@ -212,9 +311,13 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dWs, int ld, size_
 // (dgrad, K-major in the fan-out; may be null), bias[npad]
 __global__ void repack_dense_kernel(const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                                     const float* __restrict__ b2, int k, int n, int n1, int kpad, int npad, float* __restrict__ wt,
-                                    float* __restrict__ wp, float* __restrict__ bias) {
+                                    float* __restrict__ wp, float* __restrict__ bias, const float* __restrict__ lns_src,
+                                    const float* __restrict__ lnb_src, float* __restrict__ lns, float* __restrict__ lnb) {
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx < size_t(n)) bias[idx] = idx < size_t(n1) ? b1[idx] : b2[idx - n1];
+  if (idx < size_t(n)) {
+    bias[idx] = idx < size_t(n1) ? b1[idx] : b2[idx - n1];
+    if (lns) { lns[idx] = lns_src[idx]; lnb[idx] = lnb_src[idx]; }     // LayerNorm scale / bias ride along (were two more launches per layer)
+  }
   if (idx >= size_t(k) * n) return;
   const int i = int(idx / n), j = int(idx % n);
   const float v = j < n1 ? W1[size_t(i) * n1 + j] : W2[size_t(i) * (n - n1) + (j - n1)];
@@ -289,6 +392,7 @@ struct TmjxTrainer {
   float *params = nullptr, *grads = nullptr;
   TrainStack enc, dec, vnet;
   BwdScratch sp, sv;                   // policy (encoder + decoder) / value network
+  int bwd_smem_form = 0;               // TMJX_BWD_SMEM_FORM=1: the three-pass shared-memory row kernel everywhere (A/B)
   float *zeros = nullptr, *eps = nullptr;
   std::vector<void*> owned;
 };
@@ -320,11 +424,8 @@ static int repack_layers(std::vector<Layer>& layers, const float* flat, std::vec
     const float* b2 = L.n1 < L.n ? flat + L.off_b2 : nullptr;
     const size_t total = size_t(L.k) * L.n;
     repack_dense_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(flat + L.off_w, flat + L.off_b, W2, b2, L.k, L.n, L.n1, L.kpad, L.npad, L.wt,
-                                                                     wp ? (*wp)[l] : nullptr, L.bias);
-    if (L.ln) {
-      copy_kernel<<<(L.n + 255) / 256, 256, 0, st>>>(flat + L.off_lns, L.ln_scale, L.n);
-      copy_kernel<<<(L.n + 255) / 256, 256, 0, st>>>(flat + L.off_lnb, L.ln_bias, L.n);
-    }
+                                                                     wp ? (*wp)[l] : nullptr, L.bias, L.ln ? flat + L.off_lns : nullptr,
+                                                                     L.ln ? flat + L.off_lnb : nullptr, L.ln ? L.ln_scale : nullptr, L.ln ? L.ln_bias : nullptr);
   }
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "repack launch failed");
 }
@@ -359,8 +460,13 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     const CUtensorMap* map_dh = &s.mapDH[l + m * (1 + *which)];
     const int nblk = std::min(kBwdBlocks, (rows + kBwdWarps - 1) / kBwdWarps);
     if (L.act) {
-      ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, size_t(kBwdWarps) * 3 * L.npad * 4, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale,
-                                                                                            L.ln, c.dH, kTrainLd, c.partial, rows);
+      const size_t sm = size_t(kBwdWarps) * 3 * L.npad * 4;
+      if (L.npad <= 256 && !t->bwd_smem_form)
+        ln_silu_bwd_reg_kernel<2><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
+      else if (L.npad <= 512 && !t->bwd_smem_form)
+        ln_silu_bwd_reg_kernel<4><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
+      else
+        ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
       dim3 rg((L.n + 31) / 32, L.ln ? 3 : 1);
       colsum_reduce_kernel<<<rg, 256, 0, st>>>(c.partial, nblk, L.n, L.npad, L.n1, g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr,
                                                 L.ln ? g + L.off_lnb : nullptr);
@@ -458,6 +564,9 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
   PCU(alloc(&t->zeros, kTrainLd));
   PCU(alloc(&t->eps, size_t(max_rows) * std::max(1, pd->latent_size)));
   PCU(cudaFuncSetAttribute(ln_silu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * kTrainLd * 4));
+  PCU(cudaFuncSetAttribute(ln_silu_bwd_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * 256 * 4));
+  PCU(cudaFuncSetAttribute(ln_silu_bwd_reg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * 512 * 4));
+  if (const char* e = std::getenv("TMJX_BWD_SMEM_FORM")) t->bwd_smem_form = atoi(e);
   bool ok = true;
   auto setup = [&](TrainStack& s, std::vector<Layer>& layers, const float* x0, int ldx0, size_t base, BwdScratch* scr) -> cudaError_t {
     s.layers = &layers; s.x0 = x0; s.ldx0 = ldx0; s.param_base = base; s.scr = scr;
