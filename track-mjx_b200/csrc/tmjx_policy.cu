@@ -369,7 +369,22 @@ __device__ __forceinline__ void store_tile(const uint32_t (&v)[32], float* tile,
   __syncwarp();
 }
 
-template <int BN2>
+// MN-major operands (the wgrad GEMMs: dW = x^T dH contracts over the ROWS of two row-major matrices, so the contraction index is the
+// slow one of both operands).  The row-major matrix is read through a plain 2-D map with a 32 x 32 box, one box per 32-float MN chunk:
+// 4-row groups 512 B apart along K (SBO), MN chunks 4096 B apart (LBO); the instruction descriptor's transpose bits
+// (15: A, 16: B) select the MN-major read.  Replaces the two transposing copies per layer of the first backward pass.
+// (32-bit MN-major operands have ONE legal shared-memory layout: 128-byte rows swizzled in 32-byte atoms over groups of FOUR rows --
+//  layout type 1, TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; with the ordinary 128-byte swizzle the MMA silently produces zeros)
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int BN2, int kMN = 0>   // kMN bit 0: A operand MN-major, bit 1: B operand MN-major
 __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
                                                                      const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int Kpad,
                                                                      int act, int nk_per_split = 0, size_t y_split_stride = 0) {
@@ -420,12 +435,22 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
       asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(&bar_full[s])),
                    "r"(uint32_t(C3::kStage))
                    : "memory");
-      tma_load_2d(sa, &mapX, (kt0 + kt) * BK, m0, &bar_full[s]);
-      tma_load_2d(sb, &mapW, (kt0 + kt) * BK, n0, &bar_full[s]);
+      if (kMN & 1) {   // one 32 (K rows) x 32 (MN floats) box per MN chunk, 4096 B apart
+#pragma unroll
+        for (int b = 0; b < BM2 / 32; ++b) tma_load_2d(sa + b * 4096, &mapX, m0 + 32 * b, (kt0 + kt) * BK, &bar_full[s]);
+      } else {
+        tma_load_2d(sa, &mapX, (kt0 + kt) * BK, m0, &bar_full[s]);
+      }
+      if (kMN & 2) {
+#pragma unroll
+        for (int b = 0; b < BN2 / 32; ++b) tma_load_2d(sb + b * 4096, &mapW, n0 + 32 * b, (kt0 + kt) * BK, &bar_full[s]);
+      } else {
+        tma_load_2d(sb, &mapW, (kt0 + kt) * BK, n0, &bar_full[s]);
+      }
     }
   } else if (tid == 32) {
     // ---- MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN2 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN2 >> 3) << 17) | (uint32_t(128 >> 4) << 24) | ((kMN & 1) ? (1u << 15) : 0u) | ((kMN & 2) ? (1u << 16) : 0u);
     for (int kt = 0; kt < nk; ++kt) {
       const int s = kt % STG;
       mbar_wait(&bar_full[s], uint32_t((kt / STG) & 1));
@@ -433,10 +458,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) linear_tf32_tma_kernel(const _
       const uint32_t sa = sbase + s * C3::kStage, sb = sa + C3::kABytes;
 #pragma unroll
       for (int j = 0; j < BK / 8; ++j) {
-        const uint64_t db = make_desc_sw128(sb + j * 32);
+        const uint64_t db = (kMN & 2) ? make_desc_sw128_mn(sb + j * 1024) : make_desc_sw128(sb + j * 32);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint64_t da = make_desc_sw128(sa + h * 128 * 128 + j * 32);
+          const uint64_t da = (kMN & 1) ? make_desc_sw128_mn(sa + h * 128 * 128 + j * 1024) : make_desc_sw128(sa + h * 128 * 128 + j * 32);
           mma_tf32(tmem + uint32_t(h * BN2), da, db, idesc, (kt > 0 || j > 0) ? 1u : 0u);
         }
       }
@@ -1211,6 +1236,18 @@ static bool encode_map(CUtensorMap* m, const float* base, int rows, int cols, in
   const cuuint32_t estr[2] = {1u, 1u};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// MN-major operand map of a row-major [rows, cols] matrix (see make_desc_sw128_mn): 32 (floats) x 32 (rows) box, 128-byte swizzle in 32-byte atoms
+static bool encode_map_mn(CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {32u, 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tmjx_policy

@@ -369,6 +369,7 @@ struct TrainStack {
   std::vector<float*> H, A, wp;        // pre-activations, outputs, un-transposed padded weights per layer
   std::vector<int> kNp;                // fan-in padded to the GEMM's N tile (dgrad output width)
   std::vector<CUtensorMap> mapX, mapDH, mapWp, mapXT, mapDHT;
+  std::vector<CUtensorMap> mapXmn, mapDHmn;   // MN-major wgrad operands straight from the row-major activations / gradients (no transposing copies)
 };
 
 }  // namespace tmjx_policy
@@ -392,6 +393,7 @@ struct TmjxTrainer {
   float *params = nullptr, *grads = nullptr;
   TrainStack enc, dec, vnet;
   BwdScratch sp, sv;                   // policy (encoder + decoder) / value network
+  int wgrad_mn = 3;                    // TMJX_WGRAD_MN=0: transposing copies + K-major operands (the first form; A/B)
   int bwd_smem_form = 0;               // TMJX_BWD_SMEM_FORM=1: the three-pass shared-memory row kernel everywhere (A/B)
   float *zeros = nullptr, *eps = nullptr;
   std::vector<void*> owned;
@@ -399,7 +401,7 @@ struct TmjxTrainer {
 
 // splits > 1: split-K into `splits` output planes of plane_stride floats (see linear_tf32_tma_kernel); *splits_out = planes written
 static int train_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const float* bias, float* Y, int ldy, int M, int Kpad, int Npad,
-                      cudaStream_t st, int splits = 1, size_t plane_stride = 0, int* splits_out = nullptr) {
+                      cudaStream_t st, int splits = 1, size_t plane_stride = 0, int* splits_out = nullptr, int mn = 0) {
   int nk_per = 0, nz = 1;
   if (splits > 1) {
     const int nk = Kpad / BK;
@@ -409,10 +411,16 @@ static int train_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const fl
   if (splits_out) *splits_out = nz;
   if (Npad >= 512) {
     dim3 grid((M + 255) / 256, Npad / 256, nz);
-    linear_tf32_tma_kernel<256><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    if (mn == 3) linear_tf32_tma_kernel<256, 3><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else if (mn == 2) linear_tf32_tma_kernel<256, 2><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else if (mn == 1) linear_tf32_tma_kernel<256, 1><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else linear_tf32_tma_kernel<256><<<grid, kTmaThreads, V3<256>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
   } else {
     dim3 grid((M + 255) / 256, Npad / 128, nz);
-    linear_tf32_tma_kernel<128><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    if (mn == 3) linear_tf32_tma_kernel<128, 3><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else if (mn == 2) linear_tf32_tma_kernel<128, 2><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else if (mn == 1) linear_tf32_tma_kernel<128, 1><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
+    else linear_tf32_tma_kernel<128><<<grid, kTmaThreads, V3<128>::kSmem, st>>>(mapA, mapB, bias, Y, ldy, M, Kpad, 0, nk_per, plane_stride);
   }
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "GEMM launch failed");
 }
@@ -482,14 +490,18 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     // wgrad: dW = x^T dH
     const float* x = l == 0 ? s.x0 : s.A[l - 1];
     const int ldx = l == 0 ? s.ldx0 : (*s.layers)[l - 1].npad;
-    transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, c.xT, t->rows_ld);
-    transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, c.dhT, t->rows_ld);
+    // MN-major operands read x and dH where they lie (whole 32-row K slices: rows % 32 == 0); else two transposing copies + K-major operands
+    const int mn = rows % 32 == 0 ? t->wgrad_mn : 0;      // bit 0: x MN-major, bit 1: dH MN-major (3 = both; 1 / 2: bisecting knobs)
+    if (!(mn & 1)) transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, c.xT, t->rows_ld);
+    if (!(mn & 2)) transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, c.dhT, t->rows_ld);
     // split-K so that the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs: K = the minibatch rows is the long dimension
     const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
     const size_t plane = size_t(L.kpad) * L.npad, fit = (size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2) / plane;
     const int want = std::max(1, std::min(std::min(kWgradMaxSplits, int(fit)), 148 / tiles));
     int planes = 1;
-    int rc = train_gemm(s.mapXT[l], s.mapDHT[l], t->zeros, c.dWs, L.npad, L.k, rows32, L.npad, st, want, size_t(L.kpad) * L.npad, &planes);
+    const size_t dh_idx = L.act ? l : l + m * (1 + *which);       // dH, or the linear layer's incoming dA[which] (same indexing as mapDH)
+    int rc = train_gemm((mn & 1) ? s.mapXmn[l] : s.mapXT[l], (mn & 2) ? s.mapDHmn[dh_idx] : s.mapDHT[l], t->zeros, c.dWs, L.npad, L.k, rows32, L.npad, st, want,
+                        size_t(L.kpad) * L.npad, &planes, mn);
     if (rc) return rc;
     unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(c.dWs, L.npad, size_t(L.kpad) * L.npad, planes, L.k, L.n, L.n1,
                                                                                    g + L.off_w, L.n1 < L.n ? g + L.off_w2 : nullptr);
@@ -567,12 +579,19 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
   PCU(cudaFuncSetAttribute(ln_silu_bwd_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * 256 * 4));
   PCU(cudaFuncSetAttribute(ln_silu_bwd_reg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdWarps * 3 * 512 * 4));
   if (const char* e = std::getenv("TMJX_BWD_SMEM_FORM")) t->bwd_smem_form = atoi(e);
+  if (const char* e = std::getenv("TMJX_WGRAD_MN")) t->wgrad_mn = atoi(e);
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<128>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<128>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<256>::kSmem));
+  PCU(cudaFuncSetAttribute(linear_tf32_tma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3<128>::kSmem));
   bool ok = true;
   auto setup = [&](TrainStack& s, std::vector<Layer>& layers, const float* x0, int ldx0, size_t base, BwdScratch* scr) -> cudaError_t {
     s.layers = &layers; s.x0 = x0; s.ldx0 = ldx0; s.param_base = base; s.scr = scr;
     const size_t m = layers.size();
     s.H.resize(m); s.A.resize(m); s.wp.resize(m); s.kNp.resize(m);
-    s.mapX.resize(m); s.mapDH.resize(3 * m); s.mapWp.resize(m); s.mapXT.resize(m); s.mapDHT.resize(m);
+    s.mapX.resize(m); s.mapDH.resize(3 * m); s.mapWp.resize(m); s.mapXT.resize(m); s.mapDHT.resize(m); s.mapXmn.resize(m); s.mapDHmn.resize(3 * m);
     for (size_t l = 0; l < m; ++l) {
       Layer& L = layers[l];
       if (L.npad > kTrainLd || L.kpad > kTrainLd) return cudaErrorInvalidValue;
@@ -593,6 +612,9 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
       ok = ok && encode_map(&s.mapWp[l], s.wp[l], s.kNp[l], L.npad, L.npad, s.kNp[l] >= 512 ? 256 : 128);
       ok = ok && encode_map(&s.mapXT[l], scr->xT, L.kpad, t->rows_ld, t->rows_ld, 256);
       ok = ok && encode_map(&s.mapDHT[l], scr->dhT, L.npad, t->rows_ld, t->rows_ld, L.npad >= 512 ? 256 : 128);
+      ok = ok && encode_map_mn(&s.mapXmn[l], x, max_rows, L.kpad, ldx);
+      const float* dsrc[3] = {scr->dH, scr->dA[0], scr->dA[1]};
+      for (int q = 0; q < 3; ++q) ok = ok && encode_map_mn(&s.mapDHmn[l + q * m], dsrc[q], max_rows, L.npad, kTrainLd);
     }
     return cudaSuccess;
   };
