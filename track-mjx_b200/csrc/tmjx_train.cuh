@@ -369,6 +369,7 @@ struct TrainStack {
   std::vector<float*> H, A, wp;        // pre-activations, outputs, un-transposed padded weights per layer
   std::vector<int> kNp;                // fan-in padded to the GEMM's N tile (dgrad output width)
   std::vector<CUtensorMap> mapX, mapDH, mapWp, mapXT, mapDHT;
+  std::vector<float*> dWs, partial;   // per layer: split-K planes of the wgrad GEMM, per-block column-sum partials (reduced once per stack)
   std::vector<CUtensorMap> mapXmn, mapDHmn;   // MN-major wgrad operands straight from the row-major activations / gradients (no transposing copies)
 };
 
@@ -400,6 +401,59 @@ struct TmjxTrainer {
 };
 
 // splits > 1: split-K into `splits` output planes of plane_stride floats (see linear_tf32_tma_kernel); *splits_out = planes written
+
+// ---- per-stack batched forms of the small per-layer kernels (one launch per stack instead of one per layer: a 10240-row minibatch
+// update was ~60 launches of 5 - 9 us each for column sums, split-K unpacking and operand repacking).  blockIdx.z / .y = the layer;
+// the arithmetic and its order are those of the per-layer kernels above.
+constexpr int kMaxStackLayers = 12;
+struct ColsumTask { const float* partial; float *d_bias, *d_bias2, *d_lns, *d_lnb; int nblk, n, npad, n1, nk; };
+struct ColsumTable { ColsumTask t[kMaxStackLayers]; };
+__global__ void __launch_bounds__(256) colsum_all_kernel(const __grid_constant__ ColsumTable T) {
+  const ColsumTask& q = T.t[blockIdx.z];
+  if (int(blockIdx.y) >= q.nk || int(blockIdx.x) * 32 >= q.n) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx, k = blockIdx.y;
+  float t = 0.f;
+  if (c < q.n)
+    for (int b = ty; b < q.nblk; b += 8) t += q.partial[(size_t(b) * 3 + k) * q.npad + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty != 0 || c >= q.n) return;
+  float* dst = k == 0 ? (c < q.n1 ? q.d_bias : q.d_bias2) : (k == 1 ? q.d_lns : q.d_lnb);
+  if (!dst) return;
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a += red[j][tx];
+  dst[k == 0 && c >= q.n1 ? c - q.n1 : c] = a;
+}
+struct UnpackTask { const float* dWs; float *g1, *g2; size_t plane_stride; int ld, planes, k, n, n1; };
+struct UnpackTable { UnpackTask t[kMaxStackLayers]; };
+__global__ void __launch_bounds__(256) unpack_all_kernel(const __grid_constant__ UnpackTable T) {
+  const UnpackTask& q = T.t[blockIdx.y];
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(q.k) * q.n) return;
+  const int i = int(idx / q.n), j = int(idx % q.n);
+  float v = 0.f;
+  for (int z = 0; z < q.planes; ++z) v += q.dWs[size_t(z) * q.plane_stride + size_t(i) * q.ld + j];
+  if (j < q.n1) q.g1[size_t(i) * q.n1 + j] = v;
+  else q.g2[size_t(i) * (q.n - q.n1) + (j - q.n1)] = v;
+}
+struct RepackTask { const float *W1, *b1, *W2, *b2, *lns_src, *lnb_src; float *wt, *wp, *bias, *lns, *lnb; int k, n, n1, kpad, npad; };
+struct RepackTable { RepackTask t[kMaxStackLayers]; };
+__global__ void __launch_bounds__(256) repack_all_kernel(const __grid_constant__ RepackTable T) {
+  const RepackTask& q = T.t[blockIdx.y];
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < size_t(q.n)) {
+    q.bias[idx] = idx < size_t(q.n1) ? q.b1[idx] : q.b2[idx - q.n1];
+    if (q.lns) { q.lns[idx] = q.lns_src[idx]; q.lnb[idx] = q.lnb_src[idx]; }
+  }
+  if (idx >= size_t(q.k) * q.n) return;
+  const int i = int(idx / q.n), j = int(idx % q.n);
+  const float v = j < q.n1 ? q.W1[size_t(i) * q.n1 + j] : q.W2[size_t(i) * (q.n - q.n1) + (j - q.n1)];
+  q.wt[size_t(j) * q.kpad + i] = v;
+  if (q.wp) q.wp[size_t(i) * q.npad + j] = v;
+}
+
 static int train_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const float* bias, float* Y, int ldy, int M, int Kpad, int Npad,
                       cudaStream_t st, int splits = 1, size_t plane_stride = 0, int* splits_out = nullptr, int mn = 0) {
   int nk_per = 0, nz = 1;
@@ -426,15 +480,20 @@ static int train_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const fl
 }
 
 static int repack_layers(std::vector<Layer>& layers, const float* flat, std::vector<float*>* wp, cudaStream_t st) {
+  if (layers.size() > size_t(kMaxStackLayers)) return pfail(TMJX_E_ARG, "too many layers in one stack");
+  RepackTable T;
+  size_t most = 0;
   for (size_t l = 0; l < layers.size(); ++l) {
     Layer& L = layers[l];
-    const float* W2 = L.n1 < L.n ? flat + L.off_w2 : nullptr;
-    const float* b2 = L.n1 < L.n ? flat + L.off_b2 : nullptr;
-    const size_t total = size_t(L.k) * L.n;
-    repack_dense_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(flat + L.off_w, flat + L.off_b, W2, b2, L.k, L.n, L.n1, L.kpad, L.npad, L.wt,
-                                                                     wp ? (*wp)[l] : nullptr, L.bias, L.ln ? flat + L.off_lns : nullptr,
-                                                                     L.ln ? flat + L.off_lnb : nullptr, L.ln ? L.ln_scale : nullptr, L.ln ? L.ln_bias : nullptr);
+    RepackTask& q = T.t[l];
+    q.W1 = flat + L.off_w; q.b1 = flat + L.off_b;
+    q.W2 = L.n1 < L.n ? flat + L.off_w2 : nullptr; q.b2 = L.n1 < L.n ? flat + L.off_b2 : nullptr;
+    q.lns_src = L.ln ? flat + L.off_lns : nullptr; q.lnb_src = L.ln ? flat + L.off_lnb : nullptr;
+    q.wt = L.wt; q.wp = wp ? (*wp)[l] : nullptr; q.bias = L.bias; q.lns = L.ln ? L.ln_scale : nullptr; q.lnb = L.ln ? L.ln_bias : nullptr;
+    q.k = L.k; q.n = L.n; q.n1 = L.n1; q.kpad = L.kpad; q.npad = L.npad;
+    most = std::max(most, size_t(L.k) * L.n);
   }
+  repack_all_kernel<<<dim3(unsigned((most + 255) / 256), unsigned(layers.size())), 256, 0, st>>>(T);
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "repack launch failed");
 }
 
@@ -455,11 +514,21 @@ static int stack_forward(TmjxTrainer* t, TrainStack& s, int rows, bool save, cud
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "forward launch failed");
 }
 
+// split-K planes wanted for a layer's wgrad GEMM: the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs
+static int wgrad_splits(const Layer& L) {
+  const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
+  return std::max(1, std::min(kWgradMaxSplits, 148 / tiles));
+}
+
 // backward through one stack.  dY: gradient w.r.t. the stack's output, in scr->dA[which] ([rows, kTrainLd], padding columns zero).
 // On return (need_dx) scr->dA[*which] holds the gradient w.r.t. the stack's input.
 static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, bool need_dx, cudaStream_t st) {
   BwdScratch& c = *s.scr;
   const int rows32 = (rows + 31) / 32 * 32;
+  if (s.layers->size() > size_t(kMaxStackLayers)) return pfail(TMJX_E_ARG, "too many layers in one stack");
+  ColsumTable CT;
+  UnpackTable UT;
+  size_t most = 0;
   for (int l = int(s.layers->size()) - 1; l >= 0; --l) {
     Layer& L = (*s.layers)[l];
     float* g = t->grads + s.param_base;
@@ -470,22 +539,19 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     if (L.act) {
       const size_t sm = size_t(kBwdWarps) * 3 * L.npad * 4;
       if (L.npad <= 256 && !t->bwd_smem_form)
-        ln_silu_bwd_reg_kernel<2><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
+        ln_silu_bwd_reg_kernel<2><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, s.partial[l], rows);
       else if (L.npad <= 512 && !t->bwd_smem_form)
-        ln_silu_bwd_reg_kernel<4><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
+        ln_silu_bwd_reg_kernel<4><<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, s.partial[l], rows);
       else
-        ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, c.partial, rows);
-      dim3 rg((L.n + 31) / 32, L.ln ? 3 : 1);
-      colsum_reduce_kernel<<<rg, 256, 0, st>>>(c.partial, nblk, L.n, L.npad, L.n1, g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr,
-                                                L.ln ? g + L.off_lnb : nullptr);
+        ln_silu_bwd_kernel<<<nblk, 32 * kBwdWarps, sm, st>>>(c.dA[*which], kTrainLd, s.H[l], L.npad, L.n, L.npad, L.ln_scale, L.ln, c.dH, kTrainLd, s.partial[l], rows);
+      CT.t[l] = ColsumTask{s.partial[l], g + L.off_b, nullptr, L.ln ? g + L.off_lns : nullptr, L.ln ? g + L.off_lnb : nullptr, nblk, L.n, L.npad, L.n1, L.ln ? 3 : 1};
       dh = c.dH;
       map_dh = &s.mapDH[l];
     } else {
       const int ny = std::min((rows + 7) / 8, 148);
       dim3 cg((L.n + 31) / 32, ny);
-      colsum_partial_kernel<<<cg, 256, 0, st>>>(dh, kTrainLd, L.n, L.npad, c.partial, rows);
-      colsum_reduce_kernel<<<dim3((L.n + 31) / 32, 1), 256, 0, st>>>(c.partial, ny, L.n, L.npad, L.n1, g + L.off_b,
-                                                                        L.n1 < L.n ? g + L.off_b2 : nullptr, nullptr, nullptr);
+      colsum_partial_kernel<<<cg, 256, 0, st>>>(dh, kTrainLd, L.n, L.npad, s.partial[l], rows);
+      CT.t[l] = ColsumTask{s.partial[l], g + L.off_b, L.n1 < L.n ? g + L.off_b2 : nullptr, nullptr, nullptr, ny, L.n, L.npad, L.n1, 1};
     }
     // wgrad: dW = x^T dH
     const float* x = l == 0 ? s.x0 : s.A[l - 1];
@@ -495,16 +561,14 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
     if (!(mn & 1)) transpose_kernel<<<dim3(rows32 / 32, L.kpad / 32), 256, 0, st>>>(x, ldx, rows, rows32, L.kpad, c.xT, t->rows_ld);
     if (!(mn & 2)) transpose_kernel<<<dim3(rows32 / 32, L.npad / 32), 256, 0, st>>>(dh, kTrainLd, rows, rows32, L.npad, c.dhT, t->rows_ld);
     // split-K so that the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs: K = the minibatch rows is the long dimension
-    const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
-    const size_t plane = size_t(L.kpad) * L.npad, fit = (size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2) / plane;
-    const int want = std::max(1, std::min(std::min(kWgradMaxSplits, int(fit)), 148 / tiles));
+    const int want = wgrad_splits(L);
     int planes = 1;
     const size_t dh_idx = L.act ? l : l + m * (1 + *which);       // dH, or the linear layer's incoming dA[which] (same indexing as mapDH)
-    int rc = train_gemm((mn & 1) ? s.mapXmn[l] : s.mapXT[l], (mn & 2) ? s.mapDHmn[dh_idx] : s.mapDHT[l], t->zeros, c.dWs, L.npad, L.k, rows32, L.npad, st, want,
+    int rc = train_gemm((mn & 1) ? s.mapXmn[l] : s.mapXT[l], (mn & 2) ? s.mapDHmn[dh_idx] : s.mapDHT[l], t->zeros, s.dWs[l], L.npad, L.k, rows32, L.npad, st, want,
                         size_t(L.kpad) * L.npad, &planes, mn);
     if (rc) return rc;
-    unpack_wgrad_kernel<<<unsigned((size_t(L.k) * L.n + 255) / 256), 256, 0, st>>>(c.dWs, L.npad, size_t(L.kpad) * L.npad, planes, L.k, L.n, L.n1,
-                                                                                   g + L.off_w, L.n1 < L.n ? g + L.off_w2 : nullptr);
+    UT.t[l] = UnpackTask{s.dWs[l], g + L.off_w, L.n1 < L.n ? g + L.off_w2 : nullptr, size_t(L.kpad) * L.npad, L.npad, planes, L.k, L.n, L.n1};
+    most = std::max(most, size_t(L.k) * L.n);
     // dgrad: dx = dH W^T
     if (l > 0 || need_dx) {
       rc = train_gemm(*map_dh, s.mapWp[l], t->zeros, c.dA[*which ^ 1], kTrainLd, rows, L.npad, s.kNp[l], st);
@@ -512,6 +576,10 @@ static int stack_backward(TmjxTrainer* t, TrainStack& s, int rows, int* which, b
       *which ^= 1;
     }
   }
+  // every layer's column sums and split-K planes -> the flat gradient buffer: one launch each per stack
+  const unsigned nl = unsigned(s.layers->size());
+  colsum_all_kernel<<<dim3(kTrainLd / 32, 3, nl), 256, 0, st>>>(CT);
+  unpack_all_kernel<<<dim3(unsigned((most + 255) / 256), nl), 256, 0, st>>>(UT);
   return cudaGetLastError() == cudaSuccess ? TMJX_OK : pfail(TMJX_E_CUDA, "backward launch failed");
 }
 
@@ -570,8 +638,6 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
     for (int i = 0; i < 2; ++i) PCU(alloc(&c->dA[i], size_t(max_rows) * kTrainLd));
     PCU(alloc(&c->dH, size_t(max_rows) * kTrainLd));
     PCU(alloc(&c->xT, size_t(kTrainLd) * t->rows_ld)); PCU(alloc(&c->dhT, size_t(kTrainLd) * t->rows_ld));
-    PCU(alloc(&c->dWs, size_t(kWgradMaxSplits) * kTrainLd * kTrainLd / 2));   // planes x [kpad, npad]; kpad x npad <= 1024 x 512 for every layer here
-    PCU(alloc(&c->partial, size_t(kBwdBlocks) * 3 * kTrainLd));
   }
   PCU(alloc(&t->zeros, kTrainLd));
   PCU(alloc(&t->eps, size_t(max_rows) * std::max(1, pd->latent_size)));
@@ -590,7 +656,7 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
   auto setup = [&](TrainStack& s, std::vector<Layer>& layers, const float* x0, int ldx0, size_t base, BwdScratch* scr) -> cudaError_t {
     s.layers = &layers; s.x0 = x0; s.ldx0 = ldx0; s.param_base = base; s.scr = scr;
     const size_t m = layers.size();
-    s.H.resize(m); s.A.resize(m); s.wp.resize(m); s.kNp.resize(m);
+    s.H.resize(m); s.A.resize(m); s.wp.resize(m); s.kNp.resize(m); s.dWs.resize(m); s.partial.resize(m);
     s.mapX.resize(m); s.mapDH.resize(3 * m); s.mapWp.resize(m); s.mapXT.resize(m); s.mapDHT.resize(m); s.mapXmn.resize(m); s.mapDHmn.resize(3 * m);
     for (size_t l = 0; l < m; ++l) {
       Layer& L = layers[l];
@@ -601,6 +667,10 @@ int tmjx_trainer_create(const TmjxPolicyDesc* pd, const TmjxValueDesc* vd, const
       if (L.act) { e = alloc(&s.A[l], size_t(max_rows) * L.npad); if (e != cudaSuccess) return e; }
       s.kNp[l] = L.k > 256 ? pad_to(L.k, 256) : pad_to(L.k, 128);
       e = alloc(&s.wp[l], size_t(s.kNp[l]) * L.npad);
+      if (e != cudaSuccess) return e;
+      e = alloc(&s.dWs[l], size_t(wgrad_splits(L)) * L.kpad * L.npad);
+      if (e != cudaSuccess) return e;
+      e = alloc(&s.partial[l], size_t(kBwdBlocks) * 3 * L.npad);
       if (e != cudaSuccess) return e;
       const float* x = l == 0 ? x0 : s.A[l - 1];
       const int ldx = l == 0 ? ldx0 : layers[l - 1].npad;
