@@ -159,3 +159,33 @@ def test_optimiser_step_reaches_the_acting_policy():
     _, ex2 = fresh.act(obs, ez, ea)
     assert torch.equal(ex2["logits"], ex1["logits"])
     tr.close(); pol.close(); fresh.close()
+
+
+def test_mn_major_wgrad_equals_the_transposing_form(monkeypatch):
+    """The wgrad GEMMs read x and dH through MN-major tcgen05 operands (32-byte-atom swizzle, transpose bits in the instruction
+    descriptor; csrc/tmjx_policy.cu `make_desc_sw128_mn`) instead of transposing both into K-major copies first.  Same MMAs over the same
+    K order and the same split-K plane order: the parameter gradients must agree with the transposing form (TMJX_WGRAD_MN=0) to rounding,
+    and the two per-operand bisecting modes as well."""
+    cfg = P.IntentionNetworkConfig()
+    p, v = perturbed(cfg, 9)
+    rows = 384
+    rng = np.random.default_rng(11)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    obs, eps = rng.normal(size=(rows, cfg.obs_size)).astype(np.float32), rng.normal(size=(rows, cfg.latent_size)).astype(np.float32)
+    d_logits = (rng.normal(size=(rows, 2 * cfg.action_size)) / rows).astype(np.float32)
+    d_mean = (rng.normal(size=(rows, cfg.latent_size)) / rows).astype(np.float32)
+    d_logvar = (rng.normal(size=(rows, cfg.latent_size)) / rows).astype(np.float32)
+    d_value = (rng.normal(size=rows) / rows).astype(np.float32)
+    grads = {}
+    for mode in ("0", "1", "2", "3"):
+        monkeypatch.setenv("TMJX_WGRAD_MN", mode)
+        tr = Trainer(cfg, p, v, VALUE_LAYERS, max_rows=rows)
+        tr.policy_forward(cu(obs), cu(eps)); tr.value_forward(cu(obs))
+        tr.value_backward(cu(d_value)); tr.policy_backward(cu(d_logits), cu(d_mean), cu(d_logvar))
+        torch.cuda.synchronize()
+        grads[mode] = tr.grads.clone()
+        tr.close()
+    ref = grads["0"]
+    assert ref.abs().max().item() > 1e-3
+    for mode in ("1", "2", "3"):
+        assert (grads[mode] - ref).abs().max().item() <= 1e-6 * ref.abs().max().item(), mode

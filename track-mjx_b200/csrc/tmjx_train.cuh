@@ -516,8 +516,11 @@ static int stack_forward(TmjxTrainer* t, TrainStack& s, int rows, bool save, cud
 
 // split-K planes wanted for a layer's wgrad GEMM: the (M / 256) x (N / BN) output tiles x splits fill the 148 SMs
 static int wgrad_splits(const Layer& L) {
+  static const int sms = [] { const char* e = std::getenv("TMJX_WGRAD_SMS"); return e ? std::max(1, atoi(e)) : 74; }();
+  // CTAs one wgrad GEMM aims for: half the SMs -- the policy's and the critic's backward passes run side by side on two streams (148
+  // measured 2.5 % slower per update: twice the planes to write and re-read)
   const int tiles = ((L.k + 255) / 256) * (L.npad >= 512 ? L.npad / 256 : L.npad / 128);
-  return std::max(1, std::min(kWgradMaxSplits, 148 / tiles));
+  return std::max(1, std::min(kWgradMaxSplits, sms / tiles));
 }
 
 // backward through one stack.  dY: gradient w.r.t. the stack's output, in scr->dA[which] ([rows, kTrainLd], padding columns zero).
