@@ -346,7 +346,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "policy": None if policy is None else {
-            "ms_per_step": pol_ms / K, "launches_per_step": policy.launches_per_act, "kernel": "linear_tf32_tma_kernel (TMA + tcgen05 kind::tf32, TMEM accumulators) + row kernels",
+            "ms_per_step": pol_ms / K, "launches_per_step": policy.launches_per_act, "kernel": ("mlp_chain_kernel: one persistent TMA + tcgen05 kind::tf32 launch per act (csrc/tmjx_chain.cuh)" if policy.launches_per_act == 1
+                       else "linear_tf32_tma_kernel (TMA + tcgen05 kind::tf32, TMEM accumulators) + row kernels"),
             "flops_per_env_step": 5.48e6, "achieved_tflops": 5.48e6 * ENVS_PER_GPU * K / (pol_ms * 1e-3) / 1e12},
         "wall_s_timed_region": wall,
         "episode_stats": stats,
