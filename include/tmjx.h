@@ -206,7 +206,10 @@ double tmjx_fp32_peak_tflops(int device, void* stream);
  *   decoder hidden_i: W, b, LayerNorm scale, LayerNorm bias   (i = 0 .. n_decoder_layers-1);
  *   decoder output W [., 2 action_size], b.
  * Noise is supplied by the caller (eps ~ N(0,1); the reference draws it with jax.random inside the policy), so the
- * call is a pure function of its inputs.  All array arguments of tmjx_policy_act are DEVICE pointers, row-major. */
+ * call is a pure function of its inputs.  All array arguments of tmjx_policy_act are DEVICE pointers, row-major.
+ * tmjx_policy_act / tmjx_value_apply are ONE kernel launch each (csrc/tmjx_chain.cuh: 128 environments per CTA walk the whole
+ * network; tmjx_policy_launches_per_act == 1).  Environment knobs read at create time: TMJX_POLICY_FUSED=0 (per-layer launches, the
+ * A/B reference), TMJX_CHAIN_CLUSTER=2|4 (weight slices multicast over thread-block clusters). */
 #define TMJX_POLICY_MAX_LAYERS 8
 typedef struct TmjxPolicyDesc {
   int32_t obs_size, reference_obs_size, latent_size, action_size;

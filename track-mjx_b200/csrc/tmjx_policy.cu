@@ -7,7 +7,9 @@
  *   running_statistics.normalize                                     reference track_mjx/agent/masked_running_statistics.py:217-236
  *   NormalTanhDistribution (upstream brax 0.12.3 training/distribution.py: scale = softplus(raw) + 0.001, tanh bijector)
  *
- * B200 mapping: every Dense layer is one tcgen05 GEMM over the environment batch -- `tcgen05.mma.cta_group::1.kind::tf32`
+ * B200 mapping.  The ACTING path (tmjx_policy_act, tmjx_value_apply) is one persistent launch for the whole network, tmjx_chain.cuh.
+ * This file holds the per-layer form -- the training forward / backward GEMMs of tmjx_train.cuh and the A/B reference of the fused
+ * launch (TMJX_POLICY_FUSED=0): every Dense layer is one tcgen05 GEMM over the environment batch -- `tcgen05.mma.cta_group::1.kind::tf32`
  * (fp32 operands read as TF32 by the tensor core, fp32 accumulation in TMEM; XLA's default fp32 matmul precision on
  * NVIDIA GPUs is TF32 as well).  Three kernels live here, newest first:
  *   linear_tf32_tma_kernel<BN>  (default)  256 x BN tile = two M = 128 accumulators sharing one B tile, operands moved by TMA
@@ -377,11 +379,6 @@ __device__ __forceinline__ void store_tile(const uint32_t (&v)[32], float* tile,
 //  layout type 1, TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; with the ordinary 128-byte swizzle the MMA silently produces zeros)
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr) {
   return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-               : "memory");
 }
 
 template <int BN2, int kMN = 0>   // kMN bit 0: A operand MN-major, bit 1: B operand MN-major
