@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kChainStages], bar_empty[kChainStages], bar_free[kChainStages], bar_tfull[2], bar_tempty[2], bar_cready[4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 red[2][4][128];
+  __shared__ float2 red[4][128];   // single-buffered: every layer starts with an epi_barrier (bias staging), so no warp writes layer l + 1's
+                                   // partial sums before every warp has read layer l's
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -447,11 +448,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) mlp_chain_kernel(const __gri
         if (lane == 0) mbar_arrive(&bar_cready[0]);
       }
       if (L.ln) {
-        red[l & 1][g][rl] = make_float2(s1, s2);
+        red[g][rl] = make_float2(s1, s2);
         epi_barrier();
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 r2 = red[l & 1][k][rl]; t1 += r2.x; t2 += r2.y; }
+        for (int k = 0; k < 4; ++k) { const float2 r2 = red[k][rl]; t1 += r2.x; t2 += r2.y; }
         const float mean = t1 / float(L.n), var = fmaxf(0.f, t2 / float(L.n) - mean * mean);
         rs_in = rsqrtf(var + 1e-6f);
         mr_in = rs_in * mean;
